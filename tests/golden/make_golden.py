@@ -1,0 +1,207 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference; it does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference ships no tests / golden vectors, so parity is pinned by these files:
+weights and inputs come from the seeded generators in ``must3r_b200/synthetic.py`` (regenerated
+identically by the tests), outputs come from the reference's own classes
+(must3r/model/encoder.py:13 Dust3rEncoder, must3r/model/decoder.py:14 MUSt3R) and engine functions
+(must3r/engine/inference.py) on CPU fp32 with the SDPA attention branch and the PyTorch RoPE fallback
+(identical to curope in fp32 to 1.8e-7).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+# `roma` is only needed by postprocess(compute_cam=True) (engine/inference.py:38); stub it.
+sys.modules.setdefault("roma", types.ModuleType("roma"))
+
+from must3r.model import Dust3rEncoder, MUSt3R  # noqa: E402
+from must3r.model.blocks.head import ActivationType  # noqa: E402
+import must3r.engine.inference as ref_engine  # noqa: E402
+
+from must3r_b200 import synthetic as syn  # noqa: E402
+
+torch.set_grad_enabled(False)
+torch.manual_seed(0)
+
+
+def build_ref(enc_kw, dec_kw, seed=0):
+    enc = Dust3rEncoder(**enc_kw).eval()
+    dec = MUSt3R(**dec_kw).eval()
+    esd = syn.encoder_state_dict(seed, embed_dim=enc_kw.get("embed_dim", 1024), depth=enc_kw.get("depth", 24))
+    dsd = syn.decoder_state_dict(seed, enc_embed_dim=dec_kw.get("enc_embed_dim", 1024),
+                                 embed_dim=dec_kw.get("embed_dim", 768), depth=dec_kw.get("depth", 12),
+                                 output_dim=dec_kw.get("output_dim", 1792),
+                                 feedback_type=dec_kw.get("feedback_type", None))
+    enc.load_state_dict(esd, strict=True)   # also proves the synthetic key names/shapes are the reference's
+    dec.load_state_dict(dsd, strict=True)
+    return enc, dec
+
+
+TINY_ENC = dict(img_size=(64, 64), patch_size=16, embed_dim=128, depth=2, num_heads=2)
+TINY_DEC = dict(img_size=(64, 64), enc_embed_dim=128, embed_dim=128, depth=3, num_heads=2, output_dim=1792,
+                feedback_type="single_mlp", memory_mode="kv", landscape_only=False)
+
+
+def mem_arrays(prefix, mem, out):
+    vals, labels, a, b, c = mem
+    for l, v in enumerate(vals):
+        out[f"{prefix}.mem{l}"] = v.numpy()
+    out[f"{prefix}.labels"] = labels.numpy()
+    out[f"{prefix}.tail"] = np.array([a, b, c], dtype=np.int64)
+
+
+def tiny_model_golden():
+    out = {}
+    H, W = 32, 48
+    for variant, (enc_over, dec_over) in {
+        "kv": ({}, {}),
+        "normy": ({}, dict(memory_mode="norm_y")),
+        "raw": ({}, dict(memory_mode="raw")),
+        "f0": (dict(pos_embed="RoPE100_224:512"), dict(pos_embed="RoPE100_224:512")),
+        "nofb": ({}, dict(feedback_type=None)),
+        "fblin": ({}, dict(feedback_type="single_linear")),
+    }.items():
+        enc, dec = build_ref({**TINY_ENC, **enc_over}, {**TINY_DEC, **dec_over}, seed=7)
+        imgs, ts = syn.synthetic_views(5, H, W, seed=11)
+        x, pos = enc(imgs, ts)
+        out[f"{variant}.enc_x"] = x.numpy()
+        out[f"{variant}.enc_pos"] = pos.numpy()
+        # init with 2 views (decoder.py:280-285), update with 1, update with 2 (mask with Nm>0), render 5
+        mem, pm0 = dec(x[None, 0:2], pos[None, 0:2], ts[None, 0:2], None)
+        out[f"{variant}.pm_init"] = pm0.numpy()
+        mem_arrays(f"{variant}.init", mem, out)
+        mem, pm1 = dec(x[None, 2:3], pos[None, 2:3], ts[None, 2:3], mem)
+        out[f"{variant}.pm_upd1"] = pm1.numpy()
+        mem, pm2 = dec(x[None, 3:5], pos[None, 3:5], ts[None, 3:5], mem)
+        out[f"{variant}.pm_upd2"] = pm2.numpy()
+        mem_arrays(f"{variant}.final", mem, out)
+        mem_r, pmr = dec(x[None], pos[None], ts[None], mem, render=True)
+        out[f"{variant}.pm_render"] = pmr.numpy()
+        assert mem_r[0][0] is mem[0][0]
+    # single-image init: no own-mask (decoder.py:293), B=2 scenes
+    enc, dec = build_ref(TINY_ENC, TINY_DEC, seed=7)
+    imgs, ts = syn.synthetic_views(6, H, W, seed=12)
+    x, pos = enc(imgs, ts)
+    xb, pb, tb = x.view(2, 3, *x.shape[1:]), pos.view(2, 3, *pos.shape[1:]), ts.view(2, 3, 2)
+    mem, pm = dec(xb[:, :1].contiguous(), pb[:, :1].contiguous(), tb[:, :1].contiguous(), None)
+    out["b2.pm_init1"] = pm.numpy()
+    mem, pm = dec(xb[:, 1:3].contiguous(), pb[:, 1:3].contiguous(), tb[:, 1:3].contiguous(), mem)
+    out["b2.pm_upd2"] = pm.numpy()
+    mem_arrays("b2.final", mem, out)
+    _, pm = dec(xb, pb, tb, mem, render=True)
+    out["b2.pm_render"] = pm.numpy()
+    # list form with two aspect ratios (decoder.py:158): 32x48 landscape and 48x32 portrait
+    imgs_p, ts_p = syn.synthetic_views(2, 48, 32, seed=13)
+    xp, pp = enc(imgs_p, ts_p)
+    imgs_l, ts_l = syn.synthetic_views(2, H, W, seed=14)
+    xl, pl = enc(imgs_l, ts_l)
+    mem, pms = dec([xl[None], xp[None]], [pl[None], pp[None]], [ts_l[None], ts_p[None]], None)
+    out["list.pm0"], out["list.pm1"] = pms[0].numpy(), pms[1].numpy()
+    mem_arrays("list.init", mem, out)
+    mem2, pms = dec([xp[None, :1], xl[None, :1]], [pp[None, :1], pl[None, :1]], [ts_p[None, :1], ts_l[None, :1]], mem)
+    out["list.pm2"], out["list.pm3"] = pms[0].numpy(), pms[1].numpy()
+    mem_arrays("list.final", mem2, out)
+    # postprocess (engine/inference.py:16-27)
+    pp_out = ref_engine.postprocess(torch.from_numpy(out["kv.pm_render"]), ActivationType.NORM_EXP)
+    for k, v in pp_out.items():
+        out[f"kv.post.{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "tiny_model.npz"), **out)
+    print("tiny_model.npz", len(out), "arrays")
+
+
+def digest(t: torch.Tensor, max_elems=4096):
+    """Strided sample + moments of a large tensor (keeps fixtures small)."""
+    f = t.detach().float().flatten()
+    step = max(1, f.numel() // max_elems)
+    return np.concatenate([f[::step][:max_elems].numpy(),
+                           np.array([f.mean(), f.std(), f.abs().sum() / f.numel()], dtype=np.float32)])
+
+
+def full_model_golden():
+    """Full-size ViT-L encoder / ViT-B decoder (the real architecture) -> digests only."""
+    out = {}
+    for tag, (H, W, size) in {"224": (224, 224, 224), "512": (384, 512, 512)}.items():
+        enc, dec = build_ref(dict(img_size=(size, size)),
+                             dict(img_size=(size, size), feedback_type="single_mlp", memory_mode="kv",
+                                  landscape_only=False), seed=0)
+        imgs, ts = syn.synthetic_views(3, H, W, seed=2)
+        x, pos = enc(imgs, ts)
+        out[f"{tag}.enc_x"] = digest(x)
+        mem, pm = dec(x[None, :2], pos[None, :2], ts[None, :2], None)
+        out[f"{tag}.pm_init"] = digest(pm)
+        mem, pm = dec(x[None, 2:3], pos[None, 2:3], ts[None, 2:3], mem)
+        out[f"{tag}.pm_upd"] = digest(pm)
+        out[f"{tag}.mem0"] = digest(mem[0][0])
+        out[f"{tag}.mem11"] = digest(mem[0][11])
+        out[f"{tag}.labels"] = mem[1][:, ::97].numpy()
+        _, pm = dec(x[None], pos[None], ts[None], mem, render=True)
+        out[f"{tag}.pm_render"] = digest(pm)
+        print(tag, "done")
+    np.savez_compressed(os.path.join(HERE, "full_model_digest.npz"), **out)
+
+
+def engine_golden():
+    """Engine schedulers (engine/inference.py) driven with the tiny reference model."""
+    out = {}
+    enc, dec = build_ref(TINY_ENC, TINY_DEC, seed=7)
+    pp = lambda pm: ref_engine.postprocess(pm, ActivationType.NORM_EXP)  # noqa: E731
+    # 6 views, two aspect ratios interleaved
+    views = []
+    for i in range(6):
+        H, W = (32, 48) if i % 3 != 2 else (48, 32)
+        im, ts = syn.synthetic_views(1, H, W, seed=100 + i)
+        views.append((im[0], ts[0]))
+    imgs = [v[0] for v in views]
+    tss = [v[1] for v in views]
+    img_ids = [torch.tensor(i) for i in range(6)]
+    # offline: 4 keyframes in batches [2,1,1], one refinement iteration, render all 6
+    mem, pm0, pm = ref_engine.inference_multi_ar(enc, dec, imgs, img_ids, tss, [2, 1, 1], max_bs=2,
+                                                 post_process_function=pp, device="cpu", return_mem=True,
+                                                 num_refinements_iterations=1)
+    for i, d in enumerate(pm0):
+        for k, v in d.items():
+            out[f"multi_ar.pm0.{i}.{k}"] = v.numpy()
+    for i, d in enumerate(pm):
+        for k, v in d.items():
+            out[f"multi_ar.pm.{i}.{k}"] = v.numpy()
+    mem_arrays("multi_ar.mem", mem, out)
+    # video: rolling window of 2, keyframe iff id % 3 == 0 (engine/inference.py:236)
+    mem, pm0 = ref_engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], max_bs=None,
+                                                  post_process_function=pp, device="cpu", return_mem=True,
+                                                  local_context_size=2)
+    for i, d in enumerate(pm0):
+        for k, v in d.items():
+            out[f"video.pm0.{i}.{k}"] = v.numpy()
+    mem_arrays("video.mem", mem, out)
+    # tensor path `inference` (engine/inference.py:595) with B=2 scenes of 4 views, chunked render
+    im, ts = syn.synthetic_views(8, 32, 48, seed=200)
+    pm0, pm = ref_engine.inference(enc, dec, im.view(2, 4, 3, 32, 48), ts.view(2, 4, 2), [2, 1, 1], max_bs=3)
+    out["inference.pm0"], out["inference.pm"] = pm0.numpy(), pm.numpy()
+    pm0b, pmb = ref_engine.inference(enc, dec, im.view(2, 4, 3, 32, 48), ts.view(2, 4, 2), [2, 1, 1], max_bs=None,
+                                     to_render=[1, 3])
+    out["inference.pm_sel"] = pmb.numpy()
+    np.savez_compressed(os.path.join(HERE, "engine.npz"), **out)
+    print("engine.npz", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["tiny", "engine", "full"]
+    if "tiny" in which:
+        tiny_model_golden()
+    if "engine" in which:
+        engine_golden()
+    if "full" in which:
+        full_model_golden()

@@ -1,0 +1,106 @@
+"""Pin the CPU oracle (oracle/must3r_oracle.py) against outputs of the unmodified reference
+(tests/golden/*.npz, made by tests/golden/make_golden.py).  fp32 vs fp32 on CPU: tolerance 2e-5 rel-L2
+(different op order: explicit softmax/erf vs SDPA/nn.GELU, RoPE fallback vs curope pairing)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, tiny_oracle, full_oracle, digest, rel
+from must3r_b200 import synthetic as syn
+from oracle import must3r_oracle as orc
+
+TOL = 2e-5
+
+VARIANTS = {
+    "kv": ({}, {}),
+    "normy": ({}, dict(memory_mode="norm_y")),
+    "raw": ({}, dict(memory_mode="raw")),
+    "f0": (dict(rope_f0=224 / 512), dict(rope_f0=224 / 512)),
+    "nofb": ({}, dict(feedback_type=None)),
+    "fblin": ({}, dict(feedback_type="single_linear")),
+}
+
+
+def check_mem(g, prefix, mem, depth=3):
+    for l in range(depth):
+        assert rel(mem[0][l], g[f"{prefix}.mem{l}"]) < TOL, (prefix, l)
+    assert np.array_equal(mem[1].numpy(), g[f"{prefix}.labels"])
+    assert list(mem[2:]) == g[f"{prefix}.tail"].tolist()
+
+
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_tiny_chain(variant):
+    g = load_golden("tiny_model.npz")
+    enc, dec = tiny_oracle(7, *VARIANTS[variant])
+    imgs, ts = syn.synthetic_views(5, 32, 48, seed=11)
+    x, pos = enc(imgs, ts)
+    assert rel(x, g[f"{variant}.enc_x"]) < TOL
+    assert np.array_equal(pos.numpy(), g[f"{variant}.enc_pos"])
+    mem, pm = dec(x[None, 0:2], pos[None, 0:2], ts[None, 0:2], None)
+    assert rel(pm, g[f"{variant}.pm_init"]) < TOL
+    check_mem(g, f"{variant}.init", mem)
+    mem, pm = dec(x[None, 2:3], pos[None, 2:3], ts[None, 2:3], mem)
+    assert rel(pm, g[f"{variant}.pm_upd1"]) < TOL
+    mem, pm = dec(x[None, 3:5], pos[None, 3:5], ts[None, 3:5], mem)
+    assert rel(pm, g[f"{variant}.pm_upd2"]) < TOL
+    check_mem(g, f"{variant}.final", mem)
+    mem_r, pm = dec(x[None], pos[None], ts[None], mem, render=True)
+    assert rel(pm, g[f"{variant}.pm_render"]) < TOL
+    assert mem_r[0][0] is mem[0][0]  # render returns the memory untouched (decoder.py:340)
+
+
+def test_tiny_batch2_single_image_init():
+    g = load_golden("tiny_model.npz")
+    enc, dec = tiny_oracle(7)
+    imgs, ts = syn.synthetic_views(6, 32, 48, seed=12)
+    x, pos = enc(imgs, ts)
+    xb, pb, tb = x.view(2, 3, *x.shape[1:]), pos.view(2, 3, *pos.shape[1:]), ts.view(2, 3, 2)
+    mem, pm = dec(xb[:, :1], pb[:, :1], tb[:, :1], None)
+    assert rel(pm, g["b2.pm_init1"]) < TOL
+    mem, pm = dec(xb[:, 1:3], pb[:, 1:3], tb[:, 1:3], mem)
+    assert rel(pm, g["b2.pm_upd2"]) < TOL
+    check_mem(g, "b2.final", mem)
+    _, pm = dec(xb, pb, tb, mem, render=True)
+    assert rel(pm, g["b2.pm_render"]) < TOL
+
+
+def test_tiny_list_form_two_aspect_ratios():
+    g = load_golden("tiny_model.npz")
+    enc, dec = tiny_oracle(7)
+    imgs_p, ts_p = syn.synthetic_views(2, 48, 32, seed=13)
+    xp, pp = enc(imgs_p, ts_p)
+    imgs_l, ts_l = syn.synthetic_views(2, 32, 48, seed=14)
+    xl, pl = enc(imgs_l, ts_l)
+    mem, pms = dec([xl[None], xp[None]], [pl[None], pp[None]], [ts_l[None], ts_p[None]], None)
+    assert rel(pms[0], g["list.pm0"]) < TOL and rel(pms[1], g["list.pm1"]) < TOL
+    check_mem(g, "list.init", mem)
+    mem2, pms = dec([xp[None, :1], xl[None, :1]], [pp[None, :1], pl[None, :1]], [ts_p[None, :1], ts_l[None, :1]], mem)
+    assert rel(pms[0], g["list.pm2"]) < TOL and rel(pms[1], g["list.pm3"]) < TOL
+    check_mem(g, "list.final", mem2)
+
+
+def test_postprocess():
+    g = load_golden("tiny_model.npz")
+    out = orc.postprocess(torch.from_numpy(g["kv.pm_render"]))
+    for k in ("pts3d", "pts3d_local", "conf"):
+        assert rel(out[k], g[f"kv.post.{k}"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag,H,W,size", [("224", 224, 224, 224)])
+def test_full_size_digest(tag, H, W, size):
+    """Full ViT-L / ViT-B architecture (24+12 layers) against reference digests."""
+    g = load_golden("full_model_digest.npz")
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    enc, dec = full_oracle(size)
+    imgs, ts = syn.synthetic_views(3, H, W, seed=2)
+    x, pos = enc(imgs, ts)
+    assert rel(digest(x), g[f"{tag}.enc_x"]) < TOL
+    mem, pm = dec(x[None, :2], pos[None, :2], ts[None, :2], None)
+    assert rel(digest(pm), g[f"{tag}.pm_init"]) < 5e-5
+    mem, pm = dec(x[None, 2:3], pos[None, 2:3], ts[None, 2:3], mem)
+    assert rel(digest(pm), g[f"{tag}.pm_upd"]) < 5e-5
+    assert rel(digest(mem[0][0]), g[f"{tag}.mem0"]) < 5e-5
+    assert rel(digest(mem[0][11]), g[f"{tag}.mem11"]) < 5e-5
+    assert np.array_equal(mem[1][:, ::97].numpy(), g[f"{tag}.labels"])
+    _, pm = dec(x[None], pos[None], ts[None], mem, render=True)
+    assert rel(digest(pm), g[f"{tag}.pm_render"]) < 5e-5
