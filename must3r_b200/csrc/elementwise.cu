@@ -1,0 +1,284 @@
+// HBM-bound kernels of the hot path: LayerNorm (fp32 rows -> 16-bit GEMM operand), casts, RoPE table,
+// stand-alone curope-compatible RoPE, im2col for the patch embedding, head unpatchify, postprocess.
+// All are coalesced / 16-byte vectorised; one warp per row for the row-wise ones.
+#include "ptx.cuh"
+#include "m3r_internal.h"
+
+namespace m3r {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// One warp per row; the row lives in registers (D <= 32 * 4 * MAXV). Two-pass mean / variance like torch.
+template <int MAXV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long ldx,
+                                                        const float* __restrict__ add, long long ldadd,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, int M, int D, void* __restrict__ out, long long ldo,
+                                                        int out_dtype, int is_bf16) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int nv = D >> 2;  // float4 per row
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+  const float4* ar = add ? reinterpret_cast<const float4*>(add + (long long)row * ldadd) : nullptr;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      float4 t = xr[idx];
+      if (ar) { const float4 a = ar[idx]; t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
+      v[i] = t;
+      s += (t.x + t.y) + (t.z + t.w);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / D + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int idx = lane + i * 32;
+    if (idx < nv) {
+      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      float4 y;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x;
+      y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z;
+      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      if (out_dtype == 0) {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long long)row * ldo)[idx] = y;
+      } else {
+        uint2 w;
+        w.x = pack16(y.x, y.y, is_bf16);
+        w.y = pack16(y.z, y.w, is_bf16);
+        reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out) + (long long)row * ldo)[idx] = w;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ x, long long ldx, int M, int D,
+                                                     uint16_t* __restrict__ out, long long ldo, int is_bf16) {
+  const int nv = D >> 2;
+  const long long total = (long long)M * nv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int row = int(i / nv), c = int(i % nv);
+    const float4 t = reinterpret_cast<const float4*>(x + (long long)row * ldx)[c];
+    uint2 w;
+    w.x = pack16(t.x, t.y, is_bf16);
+    w.y = pack16(t.z, t.w, is_bf16);
+    reinterpret_cast<uint2*>(out + (long long)row * ldo)[c] = w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- RoPE
+// tab[t][0..15]=cos(y*w_d) [16..31]=sin(y*w_d) [32..47]=cos(x*w_d) [48..63]=sin(x*w_d), w_d = f0 / base^(d/16)
+__global__ void rope_table_kernel(const long long* __restrict__ pos, int T, float base, float f0, float* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * 32) return;
+  const int t = i >> 5, axis = (i >> 4) & 1, d = i & 15;
+  const float inv_freq = f0 / powf(base, d / 16.0f);
+  const float ang = float(pos[2 * t + axis]) * inv_freq;
+  tab[t * 64 + axis * 32 + d] = cosf(ang);
+  tab[t * 64 + axis * 32 + 16 + d] = sinf(ang);
+}
+
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// curope contract: one thread per (token, head, pair index); fp32 trig, rounding only at the store.
+template <typename T>
+__global__ void rope2d_kernel(T* __restrict__ tok, int B, int N, int H, int D, long long sB, long long sN, long long sH,
+                              const long long* __restrict__ pos, float base, float fwd) {
+  const int Q = D >> 2;
+  const long long total = (long long)B * N * H * 2 * Q;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = int(i % Q);
+    const int axis = int((i / Q) % 2);
+    const int h = int((i / (2 * Q)) % H);
+    const long long bn = i / (2LL * Q * H);
+    const int n = int(bn % N), b = int(bn / N);
+    const float inv_freq = fwd / powf(base, d / float(Q));
+    const float ang = float(pos[(b * (long long)N + n) * 2 + axis]) * inv_freq;
+    const float c = cosf(ang), s = sinf(ang);
+    T* p = tok + b * sB + n * sN + h * sH + axis * 2 * Q + d;
+    const float u = to_f<T>(p[0]), v = to_f<T>(p[Q]);
+    p[0] = from_f<T>(u * c - v * s);
+    p[Q] = from_f<T>(v * c + u * s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- patch embed
+// out[(v*gh+py)*gw+px][c*256+i*16+j] = img[v][c][py*16+i][px*16+j]; each thread converts 4 consecutive j.
+__global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__ img, int V, int H, int W,
+                                                       uint16_t* __restrict__ out, int is_bf16) {
+  const int gw = W >> 4, gh = H >> 4;
+  const long long total = (long long)V * 3 * H * (W >> 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xq = int(i % (W >> 2));          // float4 index along the image row
+    long long r = i / (W >> 2);
+    const int y = int(r % H); r /= H;
+    const int c = int(r % 3);
+    const int v = int(r / 3);
+    const float4 t = reinterpret_cast<const float4*>(img + (((long long)v * 3 + c) * H + y) * W)[xq];
+    const int px = xq >> 2, j = (xq & 3) << 2, py = y >> 4, ii = y & 15;
+    const long long row = ((long long)v * gh + py) * gw + px;
+    uint2 w;
+    w.x = pack16(t.x, t.y, is_bf16);
+    w.y = pack16(t.z, t.w, is_bf16);
+    *reinterpret_cast<uint2*>(out + row * 768 + c * 256 + ii * 16 + j) = w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- head
+// out[v][16y+i][16x+j][c] = proj[v*N + y*gw + x][c*256 + 16i + j].  One thread per output pixel (C floats).
+__global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict__ proj, int V, int H, int W, int C,
+                                                         float* __restrict__ out) {
+  const int gw = W >> 4, gh = H >> 4;
+  const long long total = (long long)V * H * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int X = int(i % W);
+    const int Y = int((i / W) % H);
+    const int v = int(i / ((long long)W * H));
+    const long long row = ((long long)v * gh + (Y >> 4)) * gw + (X >> 4);
+    const float* src = proj + row * (long long)(C * 256) + (Y & 15) * 16 + (X & 15);
+    float* dst = out + i * C;
+    for (int c = 0; c < C; ++c) dst[c] = src[c * 256];
+  }
+}
+
+// pts = v / max(|v|,1e-8) * expm1(|v|) for channels 0:3 and 3:6; conf = 1 + exp(ch6)
+__global__ void __launch_bounds__(256) postprocess_kernel(const float* __restrict__ pm, long long P,
+                                                          float* __restrict__ pts3d, float* __restrict__ local,
+                                                          float* __restrict__ conf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+    const float* s = pm + i * 7;
+    float a[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) a[k] = s[k];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const float x = a[3 * g], y = a[3 * g + 1], z = a[3 * g + 2];
+      const float d = sqrtf(x * x + y * y + z * z);
+      const float f = expm1f(d) / fmaxf(d, 1e-8f);
+      float* o = (g == 0 ? pts3d : local) + i * 3;
+      o[0] = x * f; o[1] = y * f; o[2] = z * f;
+    }
+    conf[i] = 1.0f + expf(a[6]);
+  }
+}
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("%s launch: %s", what, cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+static int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms() * 16;
+  return int(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace m3r
+
+using namespace m3r;
+
+extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int64_t ldadd, const float* gamma,
+                             const float* beta, float eps, int32_t M, int32_t D, void* out, int64_t ldo,
+                             int32_t out_dtype, int32_t is_bf16, void* stream) {
+  if (!x || !gamma || !beta || !out) return set_error("layernorm: null pointer");
+  if (M <= 0) return 0;
+  if (D % 4 || D > 2048 || ldx % 4 || (add && ldadd % 4) || ldo % 4) return set_error("layernorm: D=%d must be a multiple of 4, <= 2048, 16B-aligned rows", D);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int wpb = 8;
+  const int grid = (M + wpb - 1) / wpb;
+  if (D <= 1024)
+    layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, ldx, add, ldadd, gamma, beta, eps, M, D, out, ldo, out_dtype, is_bf16);
+  else
+    layernorm_kernel<16><<<grid, wpb * 32, 0, s>>>(x, ldx, add, ldadd, gamma, beta, eps, M, D, out, ldo, out_dtype, is_bf16);
+  return check_launch("layernorm");
+}
+
+extern "C" int m3r_cast16(const float* x, int64_t ldx, int32_t M, int32_t D, void* out, int64_t ldo, int32_t is_bf16,
+                          void* stream) {
+  if (!x || !out) return set_error("cast16: null pointer");
+  if (M <= 0) return 0;
+  if (D % 4 || ldx % 4 || ldo % 4) return set_error("cast16: alignment");
+  cast16_kernel<<<grid_for((long long)M * (D / 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, ldx, M, D, reinterpret_cast<uint16_t*>(out), ldo, is_bf16);
+  return check_launch("cast16");
+}
+
+extern "C" int m3r_rope_table(const int64_t* pos, int32_t T, float base, float f0, float* tab, void* stream) {
+  if (!pos || !tab) return set_error("rope_table: null pointer");
+  if (T <= 0) return 0;
+  rope_table_kernel<<<(T * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(pos), T, base, f0, tab);
+  return check_launch("rope_table");
+}
+
+extern "C" int m3r_rope_2d(void* tokens, int32_t dtype, int32_t B, int32_t N, int32_t H, int32_t D, int64_t sB,
+                           int64_t sN, int64_t sH, const int64_t* pos, float base, float fwd, void* stream) {
+  if (!tokens || !pos) return set_error("rope_2d: null pointer");
+  if (D % 4) return set_error("rope_2d: token dim must be multiple of 4");   // kernels.cu:94
+  const long long total = (long long)B * N * H * (D / 2);
+  if (total <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = grid_for(total, 256);
+  const long long* p = reinterpret_cast<const long long*>(pos);
+  if (dtype == 0) rope2d_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<float*>(tokens), B, N, H, D, sB, sN, sH, p, base, fwd);
+  else if (dtype == 1) rope2d_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<__half*>(tokens), B, N, H, D, sB, sN, sH, p, base, fwd);
+  else if (dtype == 2) rope2d_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(tokens), B, N, H, D, sB, sN, sH, p, base, fwd);
+  else return set_error("rope_2d: bad dtype %d", dtype);
+  return check_launch("rope_2d");
+}
+
+extern "C" int m3r_im2col16(const float* img, int32_t V, int32_t H, int32_t W, void* out, int32_t is_bf16, void* stream) {
+  if (!img || !out) return set_error("im2col16: null pointer");
+  if (H % 16 || W % 16) return set_error("im2col16: image size (%d,%d) is not a multiple of the patch size 16", H, W);
+  if (V <= 0) return 0;
+  im2col16_kernel<<<grid_for((long long)V * 3 * H * (W / 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      img, V, H, W, reinterpret_cast<uint16_t*>(out), is_bf16);
+  return check_launch("im2col16");
+}
+
+extern "C" int m3r_unpatchify(const float* proj, int32_t V, int32_t H, int32_t W, int32_t C, float* out, void* stream) {
+  if (!proj || !out) return set_error("unpatchify: null pointer");
+  if (H % 16 || W % 16) return set_error("unpatchify: bad image size");
+  if (V <= 0) return 0;
+  unpatchify_kernel<<<grid_for((long long)V * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(proj, V, H, W, C, out);
+  return check_launch("unpatchify");
+}
+
+extern "C" int m3r_postprocess(const float* pm, int64_t P, float* pts3d, float* pts3d_local, float* conf, void* stream) {
+  if (!pm || !pts3d || !pts3d_local || !conf) return set_error("postprocess: null pointer");
+  if (P <= 0) return 0;
+  postprocess_kernel<<<grid_for(P, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pm, P, pts3d, pts3d_local, conf);
+  return check_launch("postprocess");
+}

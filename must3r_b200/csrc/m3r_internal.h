@@ -1,0 +1,24 @@
+// Internal helpers shared by the kernels of libm3r_b200.so (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include "../../include/must3r_b200.h"
+
+namespace m3r {
+
+int set_error(const char* fmt, ...);           // records the message, returns 1
+int num_sms();                                  // SM count of the current device (cached)
+void count_launch();                            // bumps the kernel-launch counter (m3r_launch_count)
+
+// 2-D TMA descriptor over a row-major 16-bit matrix: inner extent `cols` (contiguous), outer extent `rows`,
+// leading dimension `ld` elements, box = {box_cols, box_rows}, 128-byte swizzle, OOB reads return zeros.
+int make_tmap_2d(CUtensorMap* out, const void* base, int is_bf16, uint64_t cols, uint64_t rows, uint64_t ld,
+                 uint32_t box_cols, uint32_t box_rows);
+
+// 3-D variant: {cols, rows, batches}; rows beyond `rows` read as zeros even when the batch stride is larger.
+int make_tmap_3d(CUtensorMap* out, const void* base, int is_bf16, uint64_t cols, uint64_t rows, uint64_t batches,
+                 uint64_t ld, uint64_t batch_stride_elems, uint32_t box_cols, uint32_t box_rows);
+
+}  // namespace m3r

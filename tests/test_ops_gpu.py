@@ -1,0 +1,223 @@
+"""Operator-level parity of the sm_100a kernels (through the C ABI) against plain fp32 torch math on the
+same 16-bit-rounded inputs.  Tolerances (rel-L2): fp32-out GEMM 2e-5 (accumulation order only); 16-bit
+outputs add one rounding (fp16 2^-11, bf16 2^-8); attention adds the 16-bit rounding of P."""
+import math
+import os
+
+import pytest
+import torch
+
+from must3r_b200 import ops
+from must3r_b200.synthetic import rel_l2
+from oracle import must3r_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DT = [torch.float16, torch.bfloat16]
+OUT_TOL = {torch.float16: 6e-4, torch.bfloat16: 5e-3, torch.float32: 2e-5}
+
+
+def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).cuda()
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("bn", [64, 128, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 768, 128), (196, 2304, 768), (1000, 1024, 1024), (77, 256, 4096)])
+def test_gemm_plain(dtype, bn, M, N, K):
+    os.environ["M3R_GEMM_BN"] = str(bn)
+    try:
+        a, w = rnd(M, K, dtype=dtype, seed=1), rnd(N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+        bias = rnd(N, seed=3)
+        ref = a.float() @ w.float().t() + bias
+        out32 = ops.linear(a, w, bias, out_dtype=torch.float32)
+        assert rel_l2(out32, ref) < OUT_TOL[torch.float32]
+        out16 = ops.linear(a, w, bias)
+        assert out16.dtype == dtype and rel_l2(out16, ref) < OUT_TOL[dtype]
+    finally:
+        os.environ.pop("M3R_GEMM_BN", None)
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_gemm_large_persistent(dtype):
+    """More tiles than SMs: exercises the persistent loop, the smem ring wrap and the TMEM double buffer."""
+    M, N, K = 5000, 4096, 1024
+    a, w = rnd(M, K, dtype=dtype, seed=4), rnd(N, K, dtype=dtype, seed=5, scale=K ** -0.5)
+    ref = a.float() @ w.float().t()
+    out = ops.linear(a, w, None, out_dtype=torch.float32)
+    assert rel_l2(out, ref) < OUT_TOL[torch.float32]
+    # bit-level check of one far tile against a float64 dot product (fp32 accumulate: ~1e-6 abs here)
+    sl = (slice(4900, 4916), slice(4000, 4016))
+    ref64 = (a[sl[0]].double() @ w[sl[1]].double().t())
+    assert (out[sl].double() - ref64).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_gemm_epilogues(dtype):
+    M, N, K = 392, 768, 768
+    a, w = rnd(M, K, dtype=dtype, seed=6), rnd(N, K, dtype=dtype, seed=7, scale=K ** -0.5)
+    bias, res, rb = rnd(N, seed=8), rnd(M, N, seed=9), rnd(N, seed=10)
+    base = a.float() @ w.float().t() + bias
+    # GELU (exact erf form)
+    out = ops.linear(a, w, bias, act="gelu", out_dtype=torch.float32)
+    assert rel_l2(out, torch.nn.functional.gelu(base)) < 2e-5
+    # residual, in place on the fp32 stream
+    x = res.clone()
+    ops.linear(a, w, bias, residual=x, out=x)
+    assert rel_l2(x, base + res) < 2e-5
+    # image2_embed row bias: rows with (row % 196) >= 98
+    out = ops.linear(a, w, bias, rowbias=rb, rb_period=196, rb_first=98, out_dtype=torch.float32)
+    ref = base.clone()
+    rows = (torch.arange(M, device="cuda") % 196) >= 98
+    ref[rows] += rb
+    assert rel_l2(out, ref) < 2e-5
+    # append into a [B=2, cap=300, N] buffer at row offset 100 (196 rows per batch)
+    buf = torch.zeros(2, 300, N, device="cuda", dtype=dtype)
+    ops.linear(a, w, bias, out=buf.view(600, N)[100:], rows_per_batch=196, batch_stride_rows=300)
+    assert rel_l2(buf[:, 100:296].reshape(M, N), base) < OUT_TOL[dtype]
+    assert float(buf[:, :100].abs().max()) == 0 and float(buf[:, 296:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("f0", [1.0, 224 / 512])
+def test_gemm_rope_epilogue(dtype, f0):
+    """Fused qkv projection + 2-D RoPE (attention.py:92-96 + curope) on a non-square 6x9 grid, 2 views."""
+    H, D, gh, gw, V = 3, 192, 6, 9, 2
+    N = gh * gw
+    a, w = rnd(V * N, D, dtype=dtype, seed=11), rnd(3 * D, D, dtype=dtype, seed=12, scale=D ** -0.5)
+    bias = rnd(3 * D, seed=13)
+    ys, xs = torch.meshgrid(torch.arange(gh), torch.arange(gw), indexing="ij")
+    pos = torch.stack([ys, xs], -1).reshape(1, N, 2).cuda()
+    tab = ops.rope_table(pos[0].contiguous(), 100.0, f0)
+    out = ops.linear(a, w, bias, rope_tab=tab, rope_cols=2 * D, out_dtype=torch.float32)
+    qkv = (a.float() @ w.float().t() + bias).reshape(V, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    q = orc.rope2d(qkv[0], pos.expand(V, -1, -1), 100.0, f0)
+    k = orc.rope2d(qkv[1], pos.expand(V, -1, -1), 100.0, f0)
+    ref = torch.stack([q, k, qkv[2]], 0).permute(1, 3, 0, 2, 4).reshape(V * N, 3 * D)
+    assert rel_l2(out, ref) < 3e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_rope_2d_curope_contract(dtype):
+    B, N, H, D = 2, 35, 3, 64
+    qkv = rnd(B, N, 3, H, D, seed=14).to(dtype)
+    pos = torch.stack([torch.arange(N) // 7, torch.arange(N) % 7], -1)[None].expand(B, -1, -1).contiguous().cuda()
+    tok = qkv[:, :, 1]                      # strided view of the fused buffer, like the reference passes
+    ref = orc.rope2d(tok.float().permute(0, 2, 1, 3), pos, 100.0, 0.5).permute(0, 2, 1, 3)
+    ops.rope_2d(tok, pos, 100.0, 0.5)
+    tol = {torch.float32: 2e-6, torch.float16: 6e-4, torch.bfloat16: 5e-3}[dtype]
+    assert rel_l2(qkv[:, :, 1], ref) < tol
+    with pytest.raises(RuntimeError):
+        ops.rope_2d(tok[0], pos, 100.0, 1.0)
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("D", [768, 1024, 128])
+def test_layernorm(out_dtype, D):
+    M = 333
+    x, add = rnd(M, D, seed=15, scale=3.0) + 0.5, rnd(M, D, seed=16)
+    g, b = 1 + 0.1 * rnd(D, seed=17), 0.1 * rnd(D, seed=18)
+    out = ops.layernorm(x, g, b, 1e-6, out_dtype=out_dtype)
+    assert rel_l2(out, torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)) < OUT_TOL[out_dtype]
+    out = ops.layernorm(x, g, b, 1e-5, add=add, out_dtype=out_dtype)
+    assert rel_l2(out, torch.nn.functional.layer_norm(x + add, (D,), g, b, 1e-5)) < OUT_TOL[out_dtype]
+
+
+def ref_attn(q, k, v, mask=None):
+    s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
+    if mask is not None:
+        s = s.masked_fill(~mask, float("-inf"))
+    return torch.softmax(s, -1) @ v.float()
+
+
+ATT_TOL = {torch.float16: 1.5e-3, torch.bfloat16: 8e-3}
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,N", [(1, 1, 128), (2, 2, 196), (1, 12, 768), (3, 16, 300)])
+def test_self_attention(dtype, B, H, N):
+    """Self-attention straight out of the fused [B*N, 3*H*64] qkv buffer (attention.py:94-97 layout)."""
+    D = H * 64
+    qkv = rnd(B * N, 3 * D, dtype=dtype, seed=19)
+    out = ops.attention(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], B=B, H=H, Nq=N, Nk0=N)
+    t = qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4)
+    ref = ref_attn(t[0], t[1], t[2]).permute(0, 2, 1, 3).reshape(B * N, D)
+    assert rel_l2(out, ref) < ATT_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("Nm,n,N", [(0, 2, 196), (392, 1, 196), (588, 3, 196), (1536, 2, 768), (100, 2, 50)])
+def test_memory_cross_attention(dtype, Nm, n, N):
+    """Memory cross-attention in update mode: keys = stored memory [B,cap,1536] (K|V, padding filled with
+    NaN to prove rows beyond Nm are never consumed) + this step's new tokens, each view skipping its own
+    segment (decoder.py:119-139, 304-317)."""
+    B, H = 2, 12
+    D = H * 64
+    cap = Nm + 77
+    mem = torch.full((B, cap, 2 * D), float("nan"), device="cuda", dtype=dtype)
+    mem[:, :Nm] = rnd(B, Nm, 2 * D, dtype=dtype, seed=20)
+    new = rnd(B, n * N, 2 * D, dtype=dtype, seed=21)
+    q = rnd(B * n * N, D, dtype=dtype, seed=22)
+    mem2 = mem.view(B * cap, 2 * D)
+    new2 = new.view(B * n * N, 2 * D)
+    use_skip = Nm > 0 or n > 1
+    out = ops.attention(q, mem2[:, :D], mem2[:, D:], B=B * n, H=H, Nq=N, Nk0=Nm, kv_bstride0=cap,
+                        k1=new2[:, :D], v1=new2[:, D:], Nk1=n * N, kv_bstride1=n * N, kv_group=n,
+                        skip_lo=Nm, skip_step=N, skip_len=N if use_skip else 0)
+    kv = torch.cat([mem[:, :Nm], new], 1)                                  # [B, Nk, 2D]
+    Nk = kv.shape[1]
+    k = kv[..., :D].view(B, 1, Nk, H, 64).expand(B, n, Nk, H, 64).reshape(B * n, Nk, H, 64).permute(0, 2, 1, 3)
+    v = kv[..., D:].view(B, 1, Nk, H, 64).expand(B, n, Nk, H, 64).reshape(B * n, Nk, H, 64).permute(0, 2, 1, 3)
+    mask = torch.ones(B * n, 1, 1, Nk, dtype=torch.bool, device="cuda")
+    if use_skip:
+        for j in range(B * n):
+            mask[j, ..., Nm + (j % n) * N: Nm + (j % n + 1) * N] = False
+    ref = ref_attn(q.view(B * n, N, H, 64).permute(0, 2, 1, 3), k, v, mask).permute(0, 2, 1, 3).reshape(B * n * N, D)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < ATT_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_render_cross_attention_long_memory(dtype):
+    """Render mode: 4 views against a 20-view memory (Nmem = 15360), no mask, shared K/V (decoder.py:307-317)."""
+    H, N, Nm, n = 12, 768, 15360, 4
+    D = H * 64
+    mem = rnd(Nm, 2 * D, dtype=dtype, seed=23)
+    q = rnd(n * N, D, dtype=dtype, seed=24)
+    out = ops.attention(q, mem[:, :D], mem[:, D:], B=n, H=H, Nq=N, Nk0=Nm, kv_group=n)
+    k = mem[:, :D].view(1, Nm, H, 64).permute(0, 2, 1, 3)
+    v = mem[:, D:].view(1, Nm, H, 64).permute(0, 2, 1, 3)
+    ref = ref_attn(q.view(n, N, H, 64).permute(0, 2, 1, 3), k, v).permute(0, 2, 1, 3).reshape(n * N, D)
+    assert rel_l2(out, ref) < ATT_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_patch_embed_path(dtype):
+    V, H, W, Dm = 2, 48, 80, 128
+    img = rnd(V, 3, H, W, seed=25).clamp(-1, 1)
+    wconv = rnd(Dm, 3, 16, 16, seed=26, scale=768 ** -0.5)
+    bias = rnd(Dm, seed=27)
+    cols = ops.im2col16(img, dtype)
+    out = ops.linear(cols, wconv.reshape(Dm, 768).to(dtype), bias, out_dtype=torch.float32)
+    ref = torch.nn.functional.conv2d(img.to(dtype).float(), wconv.to(dtype).float(), bias, stride=16)
+    ref = ref.flatten(2).transpose(1, 2).reshape(V * 15, Dm)
+    assert rel_l2(out, ref) < 2e-5
+
+
+def test_unpatchify_and_postprocess():
+    V, H, W = 2, 32, 48
+    proj = rnd(V * 6, 1792, seed=28)
+    out = ops.unpatchify(proj, V, H, W)
+    ref = torch.nn.functional.pixel_shuffle(proj.view(V, 6, 1792).transpose(-1, -2).reshape(V, 1792, 2, 3), 16)
+    assert torch.equal(out, ref.permute(0, 2, 3, 1).contiguous())
+    pts, loc, conf = ops.postprocess_raw(out)
+    ref = orc.postprocess(out)
+    assert rel_l2(pts, ref["pts3d"]) < 1e-6 and rel_l2(loc, ref["pts3d_local"]) < 1e-6 and rel_l2(conf, ref["conf"]) < 1e-6
+
+
+def test_errors_are_loud():
+    a = torch.zeros(4, 96, device="cuda", dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="multiples of 64"):
+        ops.linear(a, torch.zeros(64, 96, device="cuda", dtype=torch.float16))
+    with pytest.raises(RuntimeError):
+        ops.linear(a.cpu(), a.cpu())
