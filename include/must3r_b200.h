@@ -135,7 +135,98 @@ int m3r_unpatchify(const float* proj, int32_t V, int32_t H, int32_t W, int32_t C
  * pm [P,7] -> pts3d [P,3], pts3d_local [P,3], conf [P]. */
 int m3r_postprocess(const float* pm, int64_t P, float* pts3d, float* pts3d_local, float* conf, void* stream);
 
-/* y[M,D] (fp32) += row-broadcast add... : x_out = x + off (fp32), used by tests only through layernorm. */
+/* ===================================================================================================
+ * Whole-model entry points: one call enqueues every kernel of a forward pass from C++ (no per-layer
+ * Python/ctypes overhead).  Weight structs hold DEVICE pointers (16-bit matrices in nn.Linear layout,
+ * fp32 biases / LayerNorm affines); the `blocks` arrays themselves live in HOST memory.
+ * ================================================================================================= */
+
+/* Block (must3r/model/blocks/layers.py:36-54): norm1, attn.{qkv,proj}, norm2, mlp.{fc1,fc2} */
+typedef struct {
+  const float* norm1_w; const float* norm1_b;
+  const void* qkv_w; const float* qkv_b;       /* [3D,D] */
+  const void* proj_w; const float* proj_b;     /* [D,D]  */
+  const float* norm2_w; const float* norm2_b;
+  const void* fc1_w; const float* fc1_b;       /* [4D,D] */
+  const void* fc2_w; const float* fc2_b;       /* [D,4D] */
+} m3r_enc_block;
+
+/* Dust3rEncoder (must3r/model/encoder.py:13-52) */
+typedef struct {
+  int32_t embed_dim, depth, num_heads, mlp_hidden;
+  float ln_eps, rope_base, rope_f0;
+  int32_t is_bf16;
+  const void* patch_w; const float* patch_b;   /* [D,768] = patch_embed.proj.weight.view(D,-1) */
+  const m3r_enc_block* blocks;                 /* host array [depth] */
+  const float* norm_w; const float* norm_b;    /* norm_enc */
+} m3r_encoder_weights;
+
+int64_t m3r_encoder_workspace_bytes(const m3r_encoder_weights* w, int32_t V, int32_t H, int32_t W);
+
+/* Dust3rEncoder.forward (encoder.py:46-52): img [V,3,H,W] fp32 -> x [V*N, D] fp32.
+ * pos: [N,2] int64 (y,x) positions of ONE view's tokens (all views of a call share the grid). */
+int m3r_encoder_forward(const m3r_encoder_weights* w, const float* img, int32_t V, int32_t H, int32_t W,
+                        const int64_t* pos, float* out_x, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* CachedDecoderBlock (must3r/model/blocks/layers.py:57-99), memory_mode 'kv':
+ * kv_w / kv_b = cat(cross_attn.projk, cross_attn.projv) so one GEMM emits the stored K|V row. */
+typedef struct {
+  const float* norm1_w; const float* norm1_b;
+  const void* qkv_w; const float* qkv_b;       /* [3D,D] */
+  const void* proj_w; const float* proj_b;     /* [D,D]  */
+  const float* norm2_w; const float* norm2_b;
+  const float* normy_w; const float* normy_b;
+  const void* q_w; const float* q_b;           /* cross_attn.projq [D,D] */
+  const void* kv_w; const float* kv_b;         /* [2D,D] */
+  const void* cproj_w; const float* cproj_b;   /* cross_attn.proj [D,D] */
+  const float* norm3_w; const float* norm3_b;
+  const void* fc1_w; const float* fc1_b;
+  const void* fc2_w; const float* fc2_b;
+} m3r_dec_block;
+
+/* MUSt3R (must3r/model/decoder.py:14-156) */
+typedef struct {
+  int32_t enc_dim, embed_dim, depth, num_heads, mlp_hidden, out_dim;
+  float ln_eps, fb_ln_eps, rope_base, rope_f0;
+  int32_t is_bf16;
+  int32_t feedback;                            /* 0 none, 1 single_mlp, 2 single_linear */
+  const void* embed_w; const float* embed_b;   /* feat_embed_enc_to_dec [D,enc_dim] */
+  const float* image2_embed;                   /* [D] */
+  const m3r_dec_block* blocks;                 /* host array [depth] */
+  const float* fbn_w; const float* fbn_b;      /* feedback_norm */
+  const void* fb1_w; const float* fb1_b;       /* feedback_layer.fc1 [4D,D] (or the single linear [D,D]) */
+  const void* fb2_w; const float* fb2_b;       /* feedback_layer.fc2 [D,4D] */
+  const float* normd_w; const float* normd_b;  /* norm_dec */
+  const void* head_w; const float* head_b;     /* head_dec.proj [out_dim,D] */
+} m3r_decoder_weights;
+
+/* One aspect-ratio group of a decoder call (MUSt3R.forward_list, decoder.py:158): B scenes x n_views views */
+typedef struct {
+  int32_t n_views, N, H, W;
+  const float* x_enc;      /* [B*n_views*N, enc_dim] fp32 encoder features */
+  const int64_t* pos;      /* [B*n_views*N, 2] int64 */
+  float* pointmaps;        /* out: [B*n_views, H, W, out_dim/256] fp32 */
+} m3r_dec_group;
+
+typedef struct {
+  int32_t B, G;
+  const m3r_dec_group* groups;     /* host array [G] */
+  int32_t Nm;                      /* memory tokens per scene before this call */
+  const void* const* mem;          /* host array [depth] of device ptrs: [B, >=Nm, 2D] 16-bit (NULL if Nm==0) */
+  int64_t mem_bstride_rows;        /* rows between consecutive scenes in mem[l] */
+  int32_t render;                  /* 1: read-only pass (decoder.py:307); 0: memory update */
+  int32_t is_init;                 /* current_mem is None: view 0 of group 0 gets no image2_embed (decoder.py:176,280) */
+  void* const* mem_out;            /* update only: host array [depth] of device ptrs [B, >=Nm+Nt, 2D]; rows [0,Nm) are
+                                      copied from mem[l] unless mem_out[l]==mem[l]; the new rows follow */
+  int64_t mem_out_bstride_rows;
+} m3r_decoder_call;
+
+int64_t m3r_decoder_workspace_bytes(const m3r_decoder_weights* w, const m3r_decoder_call* call);
+
+/* MUSt3R.forward / forward_list (decoder.py:158-350) for memory_mode 'kv'. */
+int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decoder_call* call, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+
 
 #ifdef __cplusplus
 }

@@ -70,13 +70,19 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m must3r_b200.build` "
                                "(must3r_b200 has no CPU / PyTorch fallback)")
-        l = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(l, name)
-            fn.restype = res
-            fn.argtypes = args
-        _lib = l
+        _lib = C.CDLL(LIB_PATH)
+        apply_signatures()
     return _lib
+
+
+def apply_signatures():
+    """(Re)apply SIGNATURES to the loaded library (model/common.py registers the whole-model entry points)."""
+    if _lib is None:
+        return
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(_lib, name)
+        fn.restype = res
+        fn.argtypes = args
 
 
 def check(rc: int, what: str = ""):

@@ -1,0 +1,304 @@
+// Whole-model forward passes: every kernel of an encoder / decoder call is enqueued from here, so a step costs
+// one C-ABI call instead of ~15 Python->ctypes round trips per layer.
+//
+// Data layout in HBM (per call, inside the caller-provided workspace):
+//   residual stream  x      fp32  [M, D]        (M = all tokens of the call, rows ordered group/scene/view/token)
+//   GEMM operands    h16    16b   [M, D]        LayerNorm output
+//                    qkv16  16b   [M, 3D]       fused q|k|v, RoPE already applied to q,k by the GEMM epilogue
+//                    att16  16b   [M, D]        attention output (heads merged), operand of proj
+//                    mlp16  16b   [M, 4D]       GELU(fc1) output
+//   decoder only     snap   fp32  [depth][M,D]  block inputs (= new_mem[l], decoder.py:304) kept for the feedback
+//                    kvnew  16b   [B, Nt, 2D]   this step's pre-feedback K|V (second key segment of the CA)
+#include <stdio.h>
+#include <vector>
+#include "m3r_internal.h"
+
+namespace m3r {
+
+struct Arena {
+  uint8_t* base; int64_t off; int64_t cap;
+  Arena(void* p, int64_t c) : base(reinterpret_cast<uint8_t*>(p)), off(0), cap(c) {}
+  template <typename T> T* take(int64_t n_elems) {
+    off = (off + 255) & ~int64_t(255);
+    T* p = reinterpret_cast<T*>(base ? base + off : nullptr);
+    off += n_elems * (int64_t)sizeof(T);
+    return p;
+  }
+};
+
+#define M3R_TRY(x) do { if ((x) != 0) return 1; } while (0)
+
+static int gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, int N, int K, int is_bf16,
+                const float* bias, int act, const float* residual, int64_t ldr, void* out, int64_t ldc, int out_dtype,
+                void* stream, const float* rope_tab = nullptr, int rope_cols = 0, int rope_period = 0,
+                const float* rowbias = nullptr, int rb_period = 1, int rb_first = 0, int rows_per_batch = 0,
+                int64_t batch_stride_rows = 0) {
+  m3r_gemm_args a;
+  a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.M = M; a.N = N; a.K = K; a.is_bf16 = is_bf16;
+  a.bias = bias; a.act = act; a.residual = residual; a.ldr = ldr;
+  a.rowbias = rowbias; a.rb_period = rb_period; a.rb_first = rb_first;
+  a.rope_tab = rope_tab; a.rope_cols = rope_cols; a.rope_period = rope_period;
+  a.out = out; a.ldc = ldc; a.out_dtype = out_dtype;
+  a.rows_per_batch = rows_per_batch; a.batch_stride_rows = batch_stride_rows;
+  return m3r_gemm(&a, stream);
+}
+
+struct EncWs { uint16_t *cols16, *h16, *qkv16, *att16, *mlp16; float *x, *rope; };
+
+static int64_t enc_layout(const m3r_encoder_weights* w, int V, int H, int W, void* base, int64_t cap, EncWs* ws) {
+  const int64_t N = (int64_t)(H / 16) * (W / 16), M = V * N, D = w->embed_dim;
+  Arena a(base, cap);
+  ws->rope = a.take<float>(N * 64);
+  ws->cols16 = a.take<uint16_t>(M * 768);
+  ws->x = a.take<float>(M * D);
+  ws->h16 = a.take<uint16_t>(M * D);
+  ws->qkv16 = a.take<uint16_t>(M * 3 * D);
+  ws->att16 = a.take<uint16_t>(M * D);
+  ws->mlp16 = a.take<uint16_t>(M * w->mlp_hidden);
+  return a.off + 256;
+}
+
+}  // namespace m3r
+
+using namespace m3r;
+
+extern "C" int64_t m3r_encoder_workspace_bytes(const m3r_encoder_weights* w, int32_t V, int32_t H, int32_t W) {
+  EncWs ws;
+  return enc_layout(w, V, H, W, nullptr, 0, &ws);
+}
+
+extern "C" int m3r_encoder_forward(const m3r_encoder_weights* w, const float* img, int32_t V, int32_t H, int32_t W,
+                                   const int64_t* pos, float* out_x, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+  if (!w || !img || !pos || !out_x || !workspace) return set_error("encoder_forward: null pointer");
+  if (H % 16 || W % 16) return set_error("Input image size (%d,%d) is not a multiple of patch size 16", H, W);  // patch_embed.py:22-23
+  if (w->embed_dim != w->num_heads * 64) return set_error("encoder_forward: head_dim must be 64");
+  if (V <= 0) return 0;
+  EncWs ws;
+  const int64_t need = enc_layout(w, V, H, W, workspace, workspace_bytes, &ws);
+  if (need > workspace_bytes) return set_error("encoder_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+  const int N = (H / 16) * (W / 16), M = V * N, D = w->embed_dim, Hh = w->num_heads, bf = w->is_bf16;
+
+  M3R_TRY(m3r_rope_table(pos, N, w->rope_base, w->rope_f0, ws.rope, stream));
+  // patch embedding = im2col + GEMM (+bias) -> fp32 residual stream
+  M3R_TRY(m3r_im2col16(img, V, H, W, ws.cols16, bf, stream));
+  M3R_TRY(gemm(ws.cols16, 768, w->patch_w, 768, M, D, 768, bf, w->patch_b, 0, nullptr, 0, ws.x, D, M3R_OUT_F32, stream));
+  for (int l = 0; l < w->depth; ++l) {
+    const m3r_enc_block& b = w->blocks[l];
+    M3R_TRY(m3r_layernorm(ws.x, D, nullptr, 0, b.norm1_w, b.norm1_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+    M3R_TRY(gemm(ws.h16, D, b.qkv_w, D, M, 3 * D, D, bf, b.qkv_b, 0, nullptr, 0, ws.qkv16, 3 * D, M3R_OUT_16, stream,
+                 ws.rope, 2 * D, N));
+    m3r_attn_args at = {};
+    at.Q = ws.qkv16; at.ldq = 3 * D;
+    at.K0 = ws.qkv16 + D; at.V0 = ws.qkv16 + 2 * D; at.ldk0 = 3 * D; at.kv_bstride0 = N; at.Nk0 = N;
+    at.O = ws.att16; at.ldo = D; at.B = V; at.H = Hh; at.Nq = N; at.kv_group = 1; at.is_bf16 = bf; at.scale = 0.125f;
+    M3R_TRY(m3r_attention(&at, stream));
+    M3R_TRY(gemm(ws.att16, D, b.proj_w, D, M, D, D, bf, b.proj_b, 0, ws.x, D, ws.x, D, M3R_OUT_F32, stream));
+    M3R_TRY(m3r_layernorm(ws.x, D, nullptr, 0, b.norm2_w, b.norm2_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+    M3R_TRY(gemm(ws.h16, D, b.fc1_w, D, M, w->mlp_hidden, D, bf, b.fc1_b, M3R_ACT_GELU, nullptr, 0, ws.mlp16,
+                 w->mlp_hidden, M3R_OUT_16, stream));
+    M3R_TRY(gemm(ws.mlp16, w->mlp_hidden, b.fc2_w, w->mlp_hidden, M, D, w->mlp_hidden, bf, b.fc2_b, 0, ws.x, D, ws.x, D,
+                 M3R_OUT_F32, stream));
+  }
+  M3R_TRY(m3r_layernorm(ws.x, D, nullptr, 0, w->norm_w, w->norm_b, w->ln_eps, M, D, out_x, D, M3R_OUT_F32, 0, stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ decoder
+namespace m3r {
+
+struct DecWs {
+  uint16_t *enc16, *h16, *qkv16, *q16, *att16, *mlp16, *kvnew;
+  float *x, *tmp, *snap, *off, *rope, *headout;
+  int64_t M, Nt;
+  std::vector<int64_t> row0;   // first row of each group
+  std::vector<int64_t> tok0;   // first new-token index (per scene) of each group
+};
+
+static int64_t dec_layout(const m3r_decoder_weights* w, const m3r_decoder_call* c, void* base, int64_t cap, DecWs* ws) {
+  const int64_t D = w->embed_dim;
+  int64_t M = 0, Nt = 0;
+  ws->row0.assign(c->G, 0); ws->tok0.assign(c->G, 0);
+  for (int g = 0; g < c->G; ++g) {
+    ws->row0[g] = M; ws->tok0[g] = Nt;
+    M += (int64_t)c->B * c->groups[g].n_views * c->groups[g].N;
+    Nt += (int64_t)c->groups[g].n_views * c->groups[g].N;
+  }
+  ws->M = M; ws->Nt = Nt;
+  Arena a(base, cap);
+  ws->rope = a.take<float>(M * 64);
+  ws->enc16 = a.take<uint16_t>(M * w->enc_dim);
+  ws->x = a.take<float>(M * D);
+  ws->tmp = a.take<float>(M * D);
+  ws->h16 = a.take<uint16_t>(M * D);
+  ws->qkv16 = a.take<uint16_t>(M * 3 * D);
+  ws->q16 = a.take<uint16_t>(M * D);
+  ws->att16 = a.take<uint16_t>(M * D);
+  const int64_t hid = w->mlp_hidden > 4 * D ? w->mlp_hidden : 4 * D;
+  ws->mlp16 = a.take<uint16_t>(M * hid);
+  ws->headout = a.take<float>(M * w->out_dim);
+  if (!c->render) {
+    ws->snap = a.take<float>((int64_t)w->depth * M * D);
+    ws->off = a.take<float>(M * D);
+    ws->kvnew = a.take<uint16_t>((int64_t)c->B * Nt * 2 * D);
+  } else {
+    ws->snap = nullptr; ws->off = nullptr; ws->kvnew = nullptr;
+  }
+  return a.off + 256;
+}
+
+}  // namespace m3r
+
+extern "C" int64_t m3r_decoder_workspace_bytes(const m3r_decoder_weights* w, const m3r_decoder_call* c) {
+  DecWs ws;
+  return dec_layout(w, c, nullptr, 0, &ws);
+}
+
+extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decoder_call* c, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+  if (!w || !c || !workspace || !c->groups) return set_error("decoder_forward: null pointer");
+  if (c->B <= 0 || c->G <= 0) return set_error("decoder_forward: empty call");
+  if (w->embed_dim != w->num_heads * 64) return set_error("decoder_forward: head_dim must be 64");
+  if (c->render && c->Nm <= 0) return set_error("decoder_forward: render needs a memory (decoder.py:278)");
+  if (c->Nm > 0 && !c->mem) return set_error("decoder_forward: memory pointers missing");
+  if (!c->render && !c->mem_out) return set_error("decoder_forward: mem_out missing");
+  DecWs ws;
+  const int64_t need = dec_layout(w, c, workspace, workspace_bytes, &ws);
+  if (need > workspace_bytes) return set_error("decoder_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+  cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
+  const int D = w->embed_dim, Hh = w->num_heads, bf = w->is_bf16, B = c->B, G = c->G, Nm = c->Nm;
+  const int M = (int)ws.M;
+  const int Nt = (int)ws.Nt;
+  int n_total = 0;
+  for (int g = 0; g < G; ++g) n_total += c->groups[g].n_views;
+  // make_mem_mask rule (decoder.py:199-204, 291-296): skip own tokens unless rendering or a lone first image
+  const bool use_skip = !c->render && (Nm > 0 || n_total > 1);
+
+  // ---- prologue: projector + image2_embed, RoPE table (decoder.py:168-187, 272-289)
+  for (int g = 0; g < G; ++g) {
+    const m3r_dec_group& gr = c->groups[g];
+    const int Mg = B * gr.n_views * gr.N;
+    if (gr.H % 16 || gr.W % 16 || (gr.H / 16) * (gr.W / 16) != gr.N) return set_error("decoder_forward: group %d: N=%d does not match true_shape (%d,%d)", g, gr.N, gr.H, gr.W);
+    M3R_TRY(m3r_rope_table(gr.pos, Mg, w->rope_base, w->rope_f0, ws.rope + ws.row0[g] * 64, stream));
+    M3R_TRY(m3r_cast16(gr.x_enc, w->enc_dim, Mg, w->enc_dim, ws.enc16 + ws.row0[g] * w->enc_dim, w->enc_dim, bf, stream));
+    const int first = (c->is_init && g == 0) ? gr.N : 0;    // rows of view 0 of every scene get no embed at init
+    M3R_TRY(gemm(ws.enc16 + ws.row0[g] * w->enc_dim, w->enc_dim, w->embed_w, w->enc_dim, Mg, D, w->enc_dim, bf, w->embed_b, 0,
+                 nullptr, 0, ws.x + ws.row0[g] * D, D, M3R_OUT_F32, stream, nullptr, 0, 0, w->image2_embed,
+                 gr.n_views * gr.N, first));
+  }
+
+  float* xcur = ws.x;
+  for (int l = 0; l < w->depth; ++l) {
+    const m3r_dec_block& b = w->blocks[l];
+    float* xin = xcur;                                   // block input X_l
+    float* xout;                                         // where X_{l+1} goes
+    if (!c->render) {
+      // new_mem[l] = X_l must survive (decoder.py:304): blocks ping through the snapshot ring
+      if (l == 0) {
+        M3R_TRY(cudaMemcpyAsync(ws.snap, xin, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, cs) != cudaSuccess ? set_error("memcpy failed") : 0);
+        xin = ws.snap;
+      }
+      xout = (l + 1 < w->depth) ? ws.snap + (int64_t)(l + 1) * M * D : ws.x;
+      // pre-feedback K|V of the new tokens -> second key segment (decoder.py:306, layers.py:81-88)
+      M3R_TRY(m3r_layernorm(xin, D, nullptr, 0, b.normy_w, b.normy_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+      for (int g = 0; g < G; ++g) {
+        const m3r_dec_group& gr = c->groups[g];
+        const int Mg = B * gr.n_views * gr.N;
+        M3R_TRY(gemm(ws.h16 + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
+                     ws.kvnew + ws.tok0[g] * 2 * D, 2 * D, M3R_OUT_16, stream, nullptr, 0, 0, nullptr, 1, 0,
+                     gr.n_views * gr.N, Nt));
+      }
+    } else {
+      xout = ws.x;
+    }
+    // ---- self-attention (layers.py:91)
+    M3R_TRY(m3r_layernorm(xin, D, nullptr, 0, b.norm1_w, b.norm1_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+    M3R_TRY(gemm(ws.h16, D, b.qkv_w, D, M, 3 * D, D, bf, b.qkv_b, 0, nullptr, 0, ws.qkv16, 3 * D, M3R_OUT_16, stream,
+                 ws.rope, 2 * D, M));
+    for (int g = 0; g < G; ++g) {
+      const m3r_dec_group& gr = c->groups[g];
+      uint16_t* qkv = ws.qkv16 + ws.row0[g] * 3 * D;
+      m3r_attn_args at = {};
+      at.Q = qkv; at.ldq = 3 * D;
+      at.K0 = qkv + D; at.V0 = qkv + 2 * D; at.ldk0 = 3 * D; at.kv_bstride0 = gr.N; at.Nk0 = gr.N;
+      at.O = ws.att16 + ws.row0[g] * D; at.ldo = D; at.B = B * gr.n_views; at.H = Hh; at.Nq = gr.N; at.kv_group = 1;
+      at.is_bf16 = bf; at.scale = 0.125f;
+      M3R_TRY(m3r_attention(&at, stream));
+    }
+    // x_tmp = X_l + proj(SA)    (out of place so X_l survives in update mode)
+    float* xt = c->render ? xin : ws.tmp;
+    M3R_TRY(gemm(ws.att16, D, b.proj_w, D, M, D, D, bf, b.proj_b, 0, xin, D, xt, D, M3R_OUT_F32, stream));
+    // ---- memory cross-attention (layers.py:92-97, attention.py:139-149): q = projq(LN2(x)), K|V = memory (+ new)
+    M3R_TRY(m3r_layernorm(xt, D, nullptr, 0, b.norm2_w, b.norm2_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+    M3R_TRY(gemm(ws.h16, D, b.q_w, D, M, D, D, bf, b.q_b, 0, nullptr, 0, ws.q16, D, M3R_OUT_16, stream));
+    for (int g = 0; g < G; ++g) {
+      const m3r_dec_group& gr = c->groups[g];
+      m3r_attn_args at = {};
+      at.Q = ws.q16 + ws.row0[g] * D; at.ldq = D;
+      const uint16_t* mem_l = Nm > 0 ? reinterpret_cast<const uint16_t*>(c->mem[l]) : nullptr;
+      if (Nm > 0) {
+        at.K0 = mem_l; at.V0 = mem_l + D; at.ldk0 = 2 * D; at.kv_bstride0 = c->mem_bstride_rows; at.Nk0 = Nm;
+        if (!c->render) { at.K1 = ws.kvnew; at.V1 = ws.kvnew + D; at.ldk1 = 2 * D; at.kv_bstride1 = Nt; at.Nk1 = Nt; }
+      } else {
+        at.K0 = ws.kvnew; at.V0 = ws.kvnew + D; at.ldk0 = 2 * D; at.kv_bstride0 = Nt; at.Nk0 = Nt;   // first call: only new tokens
+      }
+      at.O = ws.att16 + ws.row0[g] * D; at.ldo = D; at.B = B * gr.n_views; at.H = Hh; at.Nq = gr.N;
+      at.kv_group = gr.n_views; at.is_bf16 = bf; at.scale = 0.125f;
+      if (use_skip) { at.skip_lo = Nm + (int)ws.tok0[g]; at.skip_step = gr.N; at.skip_len = gr.N; }
+      M3R_TRY(m3r_attention(&at, stream));
+    }
+    M3R_TRY(gemm(ws.att16, D, b.cproj_w, D, M, D, D, bf, b.cproj_b, 0, xt, D, xt, D, M3R_OUT_F32, stream));
+    // ---- MLP (layers.py:98)
+    M3R_TRY(m3r_layernorm(xt, D, nullptr, 0, b.norm3_w, b.norm3_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+    M3R_TRY(gemm(ws.h16, D, b.fc1_w, D, M, w->mlp_hidden, D, bf, b.fc1_b, M3R_ACT_GELU, nullptr, 0, ws.mlp16, w->mlp_hidden,
+                 M3R_OUT_16, stream));
+    M3R_TRY(gemm(ws.mlp16, w->mlp_hidden, b.fc2_w, w->mlp_hidden, M, D, w->mlp_hidden, bf, b.fc2_b, 0, xt, D, xout, D,
+                 M3R_OUT_F32, stream));
+    xcur = xout;
+  }
+
+  // ---- prediction head (decoder.py:149-156, head.py:69-72): LN -> Linear(768->1792) fp32 -> pixel shuffle
+  M3R_TRY(m3r_layernorm(xcur, D, nullptr, 0, w->normd_w, w->normd_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+  M3R_TRY(gemm(ws.h16, D, w->head_w, D, M, w->out_dim, D, bf, w->head_b, 0, nullptr, 0, ws.headout, w->out_dim, M3R_OUT_F32, stream));
+  for (int g = 0; g < G; ++g) {
+    const m3r_dec_group& gr = c->groups[g];
+    M3R_TRY(m3r_unpatchify(ws.headout + ws.row0[g] * w->out_dim, B * gr.n_views, gr.H, gr.W, w->out_dim / 256, gr.pointmaps, stream));
+  }
+
+  if (!c->render) {
+    // ---- feedback (feedback_mechanism.py:39-53) and post-feedback K|V appended to the memory (decoder.py:323-330)
+    const float* off = nullptr;
+    if (w->feedback) {
+      const float* last = ws.snap + (int64_t)(w->depth - 1) * M * D;      // new_mem[-1] = input of the last block
+      M3R_TRY(m3r_layernorm(last, D, nullptr, 0, w->fbn_w, w->fbn_b, w->fb_ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+      if (w->feedback == 1) {
+        M3R_TRY(gemm(ws.h16, D, w->fb1_w, D, M, 4 * D, D, bf, w->fb1_b, M3R_ACT_GELU, nullptr, 0, ws.mlp16, 4 * D, M3R_OUT_16, stream));
+        M3R_TRY(gemm(ws.mlp16, 4 * D, w->fb2_w, 4 * D, M, D, 4 * D, bf, w->fb2_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, stream));
+      } else {
+        M3R_TRY(gemm(ws.h16, D, w->fb1_w, D, M, D, D, bf, w->fb1_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, stream));
+      }
+      off = ws.off;
+    }
+    for (int l = 0; l < w->depth; ++l) {
+      const m3r_dec_block& b = w->blocks[l];
+      uint16_t* mo = reinterpret_cast<uint16_t*>(c->mem_out[l]);
+      if (!mo) return set_error("decoder_forward: mem_out[%d] is null", l);
+      if (Nm > 0 && c->mem[l] != c->mem_out[l]) {
+        cudaError_t e = cudaMemcpy2DAsync(mo, (size_t)c->mem_out_bstride_rows * 2 * D * 2, c->mem[l],
+                                          (size_t)c->mem_bstride_rows * 2 * D * 2, (size_t)Nm * 2 * D * 2, B,
+                                          cudaMemcpyDeviceToDevice, cs);
+        if (e != cudaSuccess) return set_error("decoder_forward: memory copy failed: %s", cudaGetErrorString(e));
+      }
+      const float* add = (off && l < w->depth - 1) ? off : nullptr;        // the last level gets no offset
+      M3R_TRY(m3r_layernorm(ws.snap + (int64_t)l * M * D, D, add, D, b.normy_w, b.normy_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+      for (int g = 0; g < G; ++g) {
+        const m3r_dec_group& gr = c->groups[g];
+        const int Mg = B * gr.n_views * gr.N;
+        M3R_TRY(gemm(ws.h16 + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
+                     mo + ((int64_t)Nm + ws.tok0[g]) * 2 * D, 2 * D, M3R_OUT_16, stream, nullptr, 0, 0, nullptr, 1, 0,
+                     gr.n_views * gr.N, c->mem_out_bstride_rows));
+      }
+    }
+  }
+  return 0;
+}
