@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — views/sec of the MUSt3R multi-view inference hot path on B200 (BASELINE.json metric).
+
+Workload (BASELINE.json configs[2], "C3"): MUSt3R_512 config, 20 synthetic views 512x384 per GPU, random-init
+ViT-L encoder / ViT-B memory decoder; schedule = encode all views, memory init with 2 views, 18 sequential
+1-view memory updates, render all 20 views, raw->pts3d/conf activation.  A "step" is one pass of
+that whole job.  At N>1 GPUs the views of ONE scene are sharded (20 per GPU): sharded encoder, shard-local memory
+updates + one all-gather of the new memory tokens per update step, sharded render.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--views V] [--dtype bf16|fp16] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = device-timed views/s with inputs resident in HBM; `e2e` = same job through
+the public API from pinned HOST images to HOST results (H2D/D2H inside the timed region); `roofline` = dominant kernel
+(memory cross-attention) achieved TFLOP/s vs the measured bf16 peak; `cpu_baseline` = the CPU oracle port of the
+reference timed on this box's host cores on a bounded sample.  `--impl reference` times that CPU path alone.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 384, 512
+N_TOK = (H // 16) * (W // 16)
+
+
+def flops_per_job(V, mem_views_schedule):
+    """Algorithmic FLOPs (multiply-add = 2) of one job, SURVEY.md §8a table: encoder 523.0 GF/view; decoder
+    render 177.3 + 21.74*M GF/view (M = views attended); update adds 50.7 GF/view."""
+    enc = 523.0e9 * V
+    upd = sum(n * (177.3e9 + 50.7e9 + 21.74e9 * m) for n, m in mem_views_schedule["updates"])
+    ren = sum(n * (177.3e9 + 21.74e9 * m) for n, m in mem_views_schedule["renders"])
+    return enc + upd + ren
+
+
+class ClockSampler:
+    def __init__(self, device_index):
+        self.idx, self.rows, self._stop = device_index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=10)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_job(n_views, threads):
+    """The reference algorithm on host cores: the oracle port (oracle/must3r_oracle.py, pinned to the reference by
+    tests/golden) on a bounded sample: `n_views` views 512x384 = encoder + 2-view init + (n-2) 1-view updates +
+    render of all n views + activation."""
+    from must3r_b200 import synthetic as syn
+    from oracle import must3r_oracle as orc
+    torch.set_num_threads(threads)
+    enc = orc.OracleEncoder(syn.encoder_state_dict(0), orc.EncoderConfig(img_size=(512, 512)))
+    dec = orc.OracleDecoder(syn.decoder_state_dict(0), orc.DecoderConfig(img_size=(512, 512)))
+    imgs, ts = syn.synthetic_views(n_views, H, W, seed=2)
+
+    def job():
+        x, pos = enc(imgs, ts)
+        mem, _ = dec(x[None, :2], pos[None, :2], ts[None, :2], None)
+        for i in range(2, n_views):
+            mem, _ = dec(x[None, i:i + 1], pos[None, i:i + 1], ts[None, i:i + 1], mem)
+        _, pm = dec(x[None], pos[None], ts[None], mem, render=True)
+        return orc.postprocess(pm)
+    return job
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n = args.cpu_views
+    job = cpu_reference_job(n, threads)
+    for _ in range(args.warmup):
+        job()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        job()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = n / dt
+    sample = f"{n} views 512x384 per step (encoder + 2-view init + {n - 2} updates + render {n}), fp32, oracle port"
+    print(json.dumps({
+        "impl": "reference", "metric": "views/sec at 512x384 (ViT-L enc / ViT-B dec)", "value": v, "unit": "views/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C3: MUSt3R_512, 512x384 synthetic views, init 2 + 1-view updates + render all",
+                   "views_per_step": n},
+        "cpu_baseline": {"value": v, "unit": "views/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--views", type=int, default=20, help="views per GPU")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-views", type=int, default=3, help="views per step of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from must3r_b200 import _lib, engine, synthetic as syn
+    from must3r_b200.engine import sharded
+    from must3r_b200.model import Dust3rEncoder, MUSt3R, set_precision, ActivationType
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float16
+    set_precision(dtype)
+    enc = Dust3rEncoder(img_size=(512, 512))
+    dec = MUSt3R(img_size=(512, 512), feedback_type="single_mlp", memory_mode="kv", landscape_only=False)
+    enc.load_state_dict(syn.encoder_state_dict(0))
+    dec.load_state_dict(syn.decoder_state_dict(0))
+    enc, dec = enc.to(dev).eval(), dec.to(dev).eval()
+    V = args.views
+    imgs_host, ts_host = syn.synthetic_views(V, H, W, seed=2 + rank)
+    imgs_pinned = imgs_host.pin_memory()
+    imgs_dev, ts_dev = imgs_host.to(dev), ts_host.to(dev)
+    pp = lambda pm: engine.postprocess(pm, ActivationType.NORM_EXP)  # noqa: E731
+    lib = _lib.lib()
+
+    def job(imgs, ts, to_host=False):
+        """Public-API job: engine.encoder_multi_ar + engine.inference_multi_ar (or the sharded schedule at N>1)."""
+        if world == 1:
+            views = list(imgs.unbind(0))
+            tss = list(ts.unbind(0))
+            x, pos = engine.encoder_multi_ar(enc, views, ts, device=dev)
+            ids = [torch.tensor(i) for i in range(V)]
+            pm0, pm = engine.inference_multi_ar(enc, dec, views, ids, tss, [2] + [1] * (V - 2),
+                                                encoder_precomputed_features=(x, pos), post_process_function=pp,
+                                                device=dev, preserve_gpu_mem=to_host)
+            return pm
+        return sharded.inference_sharded(enc, dec, imgs, ts, post_process_function=pp, device=dev, to_host=to_host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        job(imgs_dev, ts_dev)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs (value)
+    launches0 = lib.m3r_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            job(imgs_dev, ts_dev)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = (lib.m3r_launch_count() - launches0) // args.steps
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = V * world / (ms / 1e3)
+
+    # ---- timed region 2: end to end from pinned host images to host results
+    job(imgs_pinned.to(dev, non_blocking=True), ts_dev, to_host=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = job(imgs_pinned.to(dev, non_blocking=True), ts_dev, to_host=True)
+    ev1.record()
+    barrier()
+    ms_e2e = ev0.elapsed_time(ev1) / args.steps
+    t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_e2e = float(t.item())
+    h2d = imgs_pinned.numel() * 4
+    d2h = sum(v.numel() * v.element_size() for d in out for v in d.values())
+
+    # ---- profiled pass: per-category kernel time (CUDA events around every launch on the launch stream)
+    roof, shares = None, None
+    if rank == 0:
+        import ctypes as C
+        lib.m3r_prof_enable(1)
+        job(imgs_dev, ts_dev)
+        torch.cuda.synchronize()
+        buf = (C.c_double * 16)()
+        lib.m3r_prof_read(buf)
+        lib.m3r_prof_enable(0)
+        cats = ["gemm", "attention", "layernorm", "other"]
+        prof = {c: {"ms": buf[i * 4], "launches": int(buf[i * 4 + 1]), "flops": buf[i * 4 + 2], "bytes": buf[i * 4 + 3]}
+                for i, c in enumerate(cats)}
+        tot_ms = sum(p["ms"] for p in prof.values()) or 1.0
+        shares = {c: round(p["ms"] / tot_ms, 4) for c, p in prof.items()}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1590.0 if not peaks else peaks.get("bf16_tflops", 1590.0)))
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.59 PFLOP/s"
+        dom = max(("gemm", "attention"), key=lambda c: prof[c]["ms"])
+        ach = prof[dom]["flops"] / (prof[dom]["ms"] * 1e-3) / 1e12 if prof[dom]["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "attn_kernel" if dom == "attention" else "gemm_kernel", "achieved": ach,
+                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "per_category": {c: {"ms": round(p["ms"], 3), "launches": p["launches"],
+                                     "tflops": (p["flops"] / (p["ms"] * 1e-3) / 1e12) if p["ms"] > 0 and p["flops"] else None}
+                                 for c, p in prof.items()}}
+        sched = {"updates": [(2, 1)] + [(1, m) for m in range(2, V)], "renders": [(V, V)]} if world == 1 else None
+        if sched:
+            roof["job_tflops"] = flops_per_job(V, sched) / (ms * 1e-3) / 1e12
+            roof["job_frac_of_peak"] = roof["job_tflops"] / peak
+
+    # ---- CPU baseline on the host cores (rank 0, N=1 only), bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cj = cpu_reference_job(args.cpu_views, threads)
+        cj()
+        t0 = time.perf_counter()
+        cj()
+        dtc = time.perf_counter() - t0
+        cpu = {"value": args.cpu_views / dtc, "unit": "views/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_views} views 512x384 (encoder + 2-view init + {args.cpu_views - 2} update(s) + render), fp32 oracle port, 1 run after 1 warm-up"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "views/sec at 512x384 (ViT-L enc / ViT-B dec)", "value": value, "unit": "views/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "C3: MUSt3R_512 config, synthetic views 512x384, random-init ViT-L enc / ViT-B dec, "
+                                   "encode all + memory init 2 views + 1-view updates + render all + activation",
+                       "views_per_gpu": V, "global_views": V * world,
+                       "parallelism": "single GPU" if world == 1 else f"views sharded over {world} GPUs, shard-local update + all-gather of new memory tokens per step",
+                       "l2": "working set (1.7 GB of 16-bit weights + activations) exceeds the 126 MB L2; no explicit flush"},
+            "e2e": {"value": V * world / (ms_e2e / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches), "kernel_time_shares": shares, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clk.summary()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

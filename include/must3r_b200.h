@@ -32,6 +32,12 @@ const char* m3r_last_error(void);
 int m3r_abi_version(void);
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long long m3r_launch_count(void);
+/* Optional per-kernel device timing for bench.py: CUDA events are recorded on the launch stream around every
+ * GEMM / attention / LayerNorm kernel while enabled.  m3r_prof_read synchronises and fills
+ * out[cat*4 + {0: ms, 1: launches, 2: algorithmic flops, 3: algorithmic bytes}], cat 0 gemm, 1 attention,
+ * 2 layernorm, 3 other (16 doubles). */
+void m3r_prof_enable(int on);
+int m3r_prof_read(double* out);
 
 /* ---------------------------------------------------------------------------------------------------
  * Linear layer y = act(x W^T + b) (+ residual) on tcgen05 tensor cores.
@@ -219,6 +225,9 @@ typedef struct {
   void* const* mem_out;            /* update only: host array [depth] of device ptrs [B, >=Nm+Nt, 2D]; rows [0,Nm) are
                                       copied from mem[l] unless mem_out[l]==mem[l]; the new rows follow */
   int64_t mem_out_bstride_rows;
+  int32_t new_only;                /* update only: 1 = mem_out[l] is [B, Nt, 2D] and receives ONLY the new post-feedback
+                                      K|V rows (no copy of the old memory) - used by the sharded schedule, where the new
+                                      tokens of all ranks are all-gathered into a pre-allocated memory buffer */
 } m3r_decoder_call;
 
 int64_t m3r_decoder_workspace_bytes(const m3r_decoder_weights* w, const m3r_decoder_call* call);

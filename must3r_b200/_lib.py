@@ -49,6 +49,8 @@ SIGNATURES = {
     "m3r_last_error": (C.c_char_p, []),
     "m3r_abi_version": (C.c_int, []),
     "m3r_launch_count": (C.c_longlong, []),
+    "m3r_prof_enable": (None, [C.c_int]),
+    "m3r_prof_read": (C.c_int, [C.POINTER(C.c_double)]),
     "m3r_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
     "m3r_layernorm": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),

@@ -345,7 +345,13 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     attr_set = true;
   }
   dim3 grid((a->Nq + AT_BM - 1) / AT_BM, a->H, a->B);
-  attn_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  {
+    const double nk_eff = (double)(a->Nk0 + a->Nk1 - a->skip_len);
+    ProfScope prof(PROF_ATTN, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
+                   2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)(a->B / a->kv_group) * (a->Nk0 + a->Nk1) * a->H * HD * 2),
+                   reinterpret_cast<cudaStream_t>(stream));
+    attn_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
   count_launch();

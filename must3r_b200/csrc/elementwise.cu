@@ -218,6 +218,7 @@ extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int6
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int wpb = 8;
   const int grid = (M + wpb - 1) / wpb;
+  ProfScope prof(PROF_LN, 0.0, (double)M * D * (4.0 + (add ? 4.0 : 0.0) + (out_dtype ? 2.0 : 4.0)), s);
   if (D <= 1024)
     layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, ldx, add, ldadd, gamma, beta, eps, M, D, out, ldo, out_dtype, is_bf16);
   else

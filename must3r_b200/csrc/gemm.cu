@@ -253,7 +253,10 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream) {
   }
   const int tiles = ((a->M + BM - 1) / BM) * (a->N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmW, p);
+  {
+    ProfScope prof(PROF_GEMM, 2.0 * a->M * (double)a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + (double)a->M * a->N * (a->out_dtype ? 2 : 4), stream);
+    gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmW, p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));
   count_launch();

@@ -12,6 +12,15 @@ int set_error(const char* fmt, ...);           // records the message, returns 1
 int num_sms();                                  // SM count of the current device (cached)
 void count_launch();                            // bumps the kernel-launch counter (m3r_launch_count)
 
+// Optional per-category device timing (m3r_prof_*): CUDA events recorded on the launch stream around each kernel.
+enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_NCAT = 4 };
+struct ProfScope {
+  int slot;
+  ProfScope(int cat, double flops, double bytes, cudaStream_t s);
+  ~ProfScope();
+  cudaStream_t stream;
+};
+
 // 2-D TMA descriptor over a row-major 16-bit matrix: inner extent `cols` (contiguous), outer extent `rows`,
 // leading dimension `ld` elements, box = {box_cols, box_rows}, 128-byte swizzle, OOB reads return zeros.
 int make_tmap_2d(CUtensorMap* out, const void* base, int is_bf16, uint64_t cols, uint64_t rows, uint64_t ld,

@@ -283,7 +283,7 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
       const m3r_dec_block& b = w->blocks[l];
       uint16_t* mo = reinterpret_cast<uint16_t*>(c->mem_out[l]);
       if (!mo) return set_error("decoder_forward: mem_out[%d] is null", l);
-      if (Nm > 0 && c->mem[l] != c->mem_out[l]) {
+      if (Nm > 0 && !c->new_only && c->mem[l] != c->mem_out[l]) {
         cudaError_t e = cudaMemcpy2DAsync(mo, (size_t)c->mem_out_bstride_rows * 2 * D * 2, c->mem[l],
                                           (size_t)c->mem_bstride_rows * 2 * D * 2, (size_t)Nm * 2 * D * 2, B,
                                           cudaMemcpyDeviceToDevice, cs);
@@ -295,7 +295,7 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
         const m3r_dec_group& gr = c->groups[g];
         const int Mg = B * gr.n_views * gr.N;
         M3R_TRY(gemm(ws.h16 + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
-                     mo + ((int64_t)Nm + ws.tok0[g]) * 2 * D, 2 * D, M3R_OUT_16, stream, nullptr, 0, 0, nullptr, 1, 0,
+                     mo + ((int64_t)(c->new_only ? 0 : Nm) + ws.tok0[g]) * 2 * D, 2 * D, M3R_OUT_16, stream, nullptr, 0, 0, nullptr, 1, 0,
                      gr.n_views * gr.N, c->mem_out_bstride_rows));
       }
     }

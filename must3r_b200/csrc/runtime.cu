@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <atomic>
+#include <vector>
 #include "m3r_internal.h"
 
 namespace m3r {
@@ -19,6 +20,24 @@ int set_error(const char* fmt, ...) {
 }
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- profiling: a ring of event pairs; disabled by default (zero overhead beyond one branch)
+struct ProfRec { cudaEvent_t a, b; int cat; double flops, bytes; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static size_t g_prof_used = 0;
+
+ProfScope::ProfScope(int cat, double flops, double bytes, cudaStream_t s) : slot(-1), stream(s) {
+  if (!g_prof_on) return;
+  if (g_prof_used == g_prof.size()) {
+    ProfRec r; cudaEventCreate(&r.a); cudaEventCreate(&r.b); r.cat = 0; r.flops = r.bytes = 0;
+    g_prof.push_back(r);
+  }
+  slot = (int)g_prof_used++;
+  g_prof[slot].cat = cat; g_prof[slot].flops = flops; g_prof[slot].bytes = bytes;
+  cudaEventRecord(g_prof[slot].a, s);
+}
+ProfScope::~ProfScope() { if (slot >= 0) cudaEventRecord(g_prof[slot].b, stream); }
 
 int num_sms() {
   static int sms = 0;
@@ -90,3 +109,22 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int is_bf16, uint64_t cols,
 extern "C" const char* m3r_last_error(void) { return m3r::g_err; }
 extern "C" int m3r_abi_version(void) { return M3R_ABI_VERSION; }
 extern "C" long long m3r_launch_count(void) { return m3r::g_launches.load(); }
+
+// Enable (1) / disable (0) per-kernel event timing; enabling clears previous records.
+extern "C" void m3r_prof_enable(int on) {
+  m3r::g_prof_on = on != 0;
+  if (on) m3r::g_prof_used = 0;
+}
+// Synchronise and sum the recorded kernels per category: out[cat*4 + {0: ms, 1: launches, 2: flops, 3: bytes}]
+extern "C" int m3r_prof_read(double* out) {
+  using namespace m3r;
+  for (int i = 0; i < PROF_NCAT * 4; ++i) out[i] = 0.0;
+  for (size_t i = 0; i < g_prof_used; ++i) {
+    if (cudaEventSynchronize(g_prof[i].b) != cudaSuccess) return set_error("prof_read: event sync failed");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_prof[i].a, g_prof[i].b);
+    double* o = out + g_prof[i].cat * 4;
+    o[0] += ms; o[1] += 1.0; o[2] += g_prof[i].flops; o[3] += g_prof[i].bytes;
+  }
+  return 0;
+}

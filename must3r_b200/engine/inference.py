@@ -1,0 +1,434 @@
+"""Engine API of the reference (must3r/engine/inference.py) re-stated for must3r_b200.
+
+Same entry points, argument meaning and observable results: ``postprocess``, ``stack_views``,
+``encoder_multi_ar``, ``inference_multi_ar_batch``, ``inference_multi_ar``, ``inference_video_multi_ar``,
+``inference_encoder``, ``inference``, ``get_Nmem``, ``unstack_pointmaps``, ``concat_preds``.  The functions
+are model-agnostic (they only call ``encoder(imgs, true_shape)`` / ``decoder(x, pos, true_shape, mem,
+render=...)``), so the CPU test-suite drives them with the oracle model and the GPU suite with the CUDA
+model.  ``compute_cam=True`` (Weiszfeld focal + Procrustes) is outside the hot path.
+"""
+from __future__ import annotations
+
+import itertools
+import math
+from collections import deque
+from contextlib import nullcontext
+
+import numpy as np
+import torch
+
+from ..model.common import ActivationType
+
+
+# --------------------------------------------------------------------------------------------- postprocess
+def _act(xyz, activation):
+    if isinstance(activation, str):
+        activation = ActivationType(activation)
+    if getattr(activation, "value", activation) == "norm_exp":
+        d = xyz.norm(dim=-1, keepdim=True)
+        return xyz / d.clip(min=1e-8) * torch.expm1(d)          # must3r/tools/geometry.py:14-18
+    if getattr(activation, "value", activation) == "linear":
+        return xyz
+    raise ValueError(f"Unknown activation: {activation}")
+
+
+def postprocess(pointmaps, pointmaps_activation=ActivationType.NORM_EXP, compute_cam=False):
+    """engine/inference.py:16-48.  7-channel CUDA pointmaps with the NORM_EXP activation take the fused
+    kernel (m3r_postprocess); everything else is evaluated with torch in fp32, like the reference."""
+    if compute_cam:
+        raise NotImplementedError("postprocess(compute_cam=True) needs roma + Weiszfeld focal estimation; "
+                                  "it is outside the must3r_b200 hot path (SURVEY.md §8f)")
+    pm = pointmaps.float()
+    act_name = getattr(pointmaps_activation, "value", pointmaps_activation)
+    if pm.is_cuda and pm.shape[-1] == 7 and act_name == "norm_exp":
+        from .. import ops
+        pts, loc, conf = ops.postprocess_raw(pm)
+        return {"pts3d": pts, "pts3d_local": loc, "conf": conf}
+    out = {"pts3d": _act(pm[..., :3], pointmaps_activation)}
+    ch = pm.shape[-1]
+    if ch >= 6:
+        out["pts3d_local"] = _act(pm[..., 3:6], pointmaps_activation)
+    if ch in (4, 7):
+        out["conf"] = 1.0 + pm[..., -1].exp()
+    return out
+
+
+# --------------------------------------------------------------------------------------------- view grouping
+def _chunks(seq, size):
+    return [seq[i:i + size] for i in range(0, len(seq), size)]
+
+
+def _split_entries(entries, max_bs):
+    out = []
+    for e in entries:
+        out.extend(_chunks(e, max_bs) if isinstance(e, list) else list(torch.split(e, max_bs)))
+    return out
+
+
+def stack_views(true_shape, values, max_bs=None):
+    """Group views by identical true_shape (engine/inference.py:65-136).
+
+    Returns ``(true_shape_stacks, index_stacks, *value_stacks)``: groups follow the lexicographic order of the
+    unique shapes (torch.unique), views keep their order inside a group; inside a group, views for which any
+    value is None (features to be recomputed) are moved to an extra group appended at the end; groups are then
+    cut in chunks of ``max_bs``; a group holding None values collapses to a single None."""
+    uniq, inverse = torch.unique(true_shape, dim=0, return_inverse=True)
+    n_groups = uniq.shape[0]
+    members = [[i for i in range(true_shape.shape[0]) if int(inverse[i]) == g] for g in range(n_groups)]
+    # peel off the views with missing values
+    extra = []
+    for g in range(n_groups):
+        missing = [any(v[i] is None for v in values) for i in members[g]]
+        if any(missing) and not all(missing):
+            extra.append([i for i, m in zip(members[g], missing) if m])
+            members[g] = [i for i, m in zip(members[g], missing) if not m]
+    members += extra
+
+    shape_stacks = [torch.stack([true_shape[i] for i in grp], dim=0) for grp in members]
+    index_stacks = [list(grp) for grp in members]
+    value_stacks = []
+    for v in values:
+        per_group = []
+        for grp in members:
+            items = [v[i] for i in grp]
+            per_group.append(items if any(it is None for it in items) else torch.stack(items, dim=0))
+        value_stacks.append(per_group)
+
+    if max_bs is not None:
+        shape_stacks = _split_entries(shape_stacks, max_bs)
+        index_stacks = [c for grp in index_stacks for c in _chunks(grp, max_bs)]
+        value_stacks = [_split_entries(vs, max_bs) for vs in value_stacks]
+    value_stacks = [[None if isinstance(e, list) and any(it is None for it in e) else e for e in vs]
+                    for vs in value_stacks]
+    return (shape_stacks, index_stacks, *value_stacks)
+
+
+def get_Nmem(mem):
+    """engine/inference.py:530-535"""
+    return 0 if mem is None else mem[1].shape[1]
+
+
+def unstack_pointmaps(index_stacks_i, pointmaps_0_i):
+    """Scatter per-group dicts of stacked tensors back to per-view dicts (engine/inference.py:538-552)."""
+    n = max(max(idx) for idx in index_stacks_i) + 1
+    out = [None] * n
+    for stack, idx in zip(pointmaps_0_i, index_stacks_i):
+        for j, view in enumerate(idx):
+            out[view] = {k: v[j] for k, v in stack.items()}
+    return out
+
+
+# --------------------------------------------------------------------------------------------- encoder / decoder steps
+@torch.no_grad()
+def encoder_multi_ar(encoder, imgs, true_shape, verbose=False, max_bs=None, device=None, preserve_gpu_mem=False):
+    """Encode a list of views of mixed aspect ratios (engine/inference.py:139-165) -> per-view (x, pos) lists."""
+    n = true_shape.shape[0]
+    device = device or true_shape.device
+    outdevice = "cpu" if preserve_gpu_mem else device
+    shape_stacks, index_stacks, img_stacks = stack_views(true_shape, [imgs], max_bs=max_bs)
+    x, pos = [None] * n, [None] * n
+    for im, ts, idx in zip(img_stacks, shape_stacks, index_stacks):
+        xs, ps = encoder(im.to(device), ts.to(device))
+        for j, view in enumerate(idx):
+            x[view] = xs[j].to(outdevice)
+            pos[view] = ps[j].to(outdevice)
+    return x, pos
+
+
+@torch.no_grad()
+def inference_multi_ar_batch(encoder, decoder, imgs, true_shape, mem=None, verbose=False,
+                             encoder_precomputed_features=None, preserve_gpu_mem=False,
+                             post_process_function=lambda x: {'pts3d': x}, device=None, render=False,
+                             viser_server=None):
+    """One decoder call over already-stacked aspect-ratio groups (engine/inference.py:168-202)."""
+    device = device or true_shape.device
+    outdevice = "cpu" if preserve_gpu_mem else device
+    if encoder_precomputed_features is None:
+        feats = [encoder(im.to(device), ts.to(device)) for im, ts in zip(imgs, true_shape)]
+        x, pos = [f[0] for f in feats], [f[1] for f in feats]
+    else:
+        x, pos = encoder_precomputed_features
+    x = [v.unsqueeze(0).to(device) for v in x]           # B = 1 scene
+    pos = [v.unsqueeze(0).to(device) for v in pos]
+    ts = [v.unsqueeze(0).to(device) for v in true_shape]
+    mem, pms = decoder(x, pos, ts, mem, render=render)
+    results = []
+    for pm in pms:
+        pm = pm.squeeze(0)
+        if post_process_function is not None:
+            pm = {k: v.to(outdevice) for k, v in post_process_function(pm).items()}
+        else:
+            pm = pm.to(outdevice)
+        results.append(pm)
+    return mem, results
+
+
+# --------------------------------------------------------------------------------------------- memory edits by label
+def _remove_from_mem(mem_values, mem_labels, idx):
+    """Drop every token labelled idx (engine/inference.py:205-213)."""
+    keep = mem_labels != idx
+    B, _, D = mem_values[0].shape
+    return [v[keep].view(B, -1, D) for v in mem_values], mem_labels[keep].view(B, -1)
+
+
+def _restore_label_in_mem(mem_labels, old_idx_to_restore, new_idx_to_remove):
+    """engine/inference.py:216-219"""
+    mem_labels[mem_labels == new_idx_to_remove] = old_idx_to_restore
+    return mem_labels
+
+
+def _update_in_mem(old_values, new_values, old_labels, new_labels, old_idx, new_idx):
+    """Overwrite the tokens labelled old_idx with those labelled new_idx (engine/inference.py:222-228)."""
+    dst, src = old_labels == old_idx, new_labels == new_idx
+    for k in range(len(old_values)):
+        old_values[k][dst] = new_values[k][src]
+    return old_values
+
+
+def _fresh_labels(new_mem, n_before):
+    return [int(v) for v in sorted(torch.unique(new_mem[1][:, n_before:]))]
+
+
+def _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device):
+    xi, pi = x[lo:hi], pos[lo:hi]
+    if None in xi or None in pi:
+        xi, pi = encoder_multi_ar(encoder, imgs[lo:hi], true_shape[lo:hi], verbose=False, max_bs=max_bs, device=device)
+        x[lo:hi], pos[lo:hi] = xi, pi
+    return xi, pi
+
+
+# --------------------------------------------------------------------------------------------- video / rolling window
+@torch.no_grad()
+def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, verbose=False, max_bs=None,
+                             encoder_precomputed_features=None, preserve_gpu_mem=False,
+                             post_process_function=lambda x: {'pts3d': x}, device=None, return_mem=False,
+                             viser_server=None, num_refinements_iterations=0, local_context_size=25,
+                             is_keyframe_function=lambda id, res, scene_state: (id % 3 == 0),
+                             scene_state=None, scene_state_update_function=lambda res, scene_state: scene_state):
+    """Streaming schedule with keyframes and a rolling window of recent frames (engine/inference.py:231-366)."""
+    true_shape = torch.stack(true_shape, dim=0)
+    n = true_shape.shape[0]
+    device = device or true_shape.device
+    x, pos = ([None] * n, [None] * n) if encoder_precomputed_features is None else encoder_precomputed_features
+    bounds = [0] + np.cumsum(mem_batches).tolist()
+    first_pass = [None] * bounds[-1]
+    mem = None
+    label_of, keyframes = {}, set()
+    window = deque()
+    for _ in range(num_refinements_iterations + 1):
+        window = deque()
+        for step in range(len(bounds) - 1):
+            lo, hi = bounds[step], bounds[step + 1]
+            ts_i, imgs_i, ids_i = true_shape[lo:hi], imgs[lo:hi], list(range(lo, hi))
+            x_i, pos_i = _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device)
+            ts_st, idx_st, x_st, pos_st, img_st = stack_views(ts_i, [x_i, pos_i, imgs_i], max_bs=max_bs)
+            n_before = get_Nmem(mem)
+            new_mem, res = inference_multi_ar_batch(encoder, decoder, img_st, ts_st, mem, verbose=verbose,
+                                                    encoder_precomputed_features=(x_st, pos_st),
+                                                    preserve_gpu_mem=preserve_gpu_mem,
+                                                    post_process_function=post_process_function, device=device,
+                                                    viser_server=viser_server)
+            res = unstack_pointmaps(idx_st, res)
+            first_pass[lo:hi] = res
+            mem = list(new_mem)
+            new_labels = _fresh_labels(mem, n_before)
+            flags = []
+            if not label_of:                       # initialisation: every view is a keyframe
+                for j, vid in enumerate(ids_i):
+                    label_of[vid] = new_labels[j]
+                    window.append(vid)
+                    keyframes.add(vid)
+                    flags.append(True)
+                    scene_state = scene_state_update_function(res[j], scene_state)
+            else:
+                for j, vid in enumerate(ids_i):
+                    seen = vid in label_of
+                    is_kf = (vid in keyframes) if seen else is_keyframe_function(vid, res[j], scene_state)
+                    window.append(vid)
+                    flags.append(is_kf)
+                    if is_kf and seen:             # refinement pass: refresh the stored tokens of this keyframe
+                        old = label_of[vid]
+                        if old != 0:               # the reference image is never refreshed
+                            mem[0] = _update_in_mem(mem[0], mem[0], mem[1], mem[1], old, new_labels[j])
+                        mem[0], mem[1] = _remove_from_mem(mem[0], mem[1], new_labels[j])
+                    elif seen:                     # known non-keyframe: keep its tokens under the old label
+                        mem[1] = _restore_label_in_mem(mem[1], label_of[vid], new_labels[j])
+                    else:
+                        label_of[vid] = new_labels[j]
+                        if is_kf:
+                            keyframes.add(vid)
+                            scene_state = scene_state_update_function(res[j], scene_state)
+            if viser_server is not None:
+                viser_server.set_views([torch.tensor(v) for v in ids_i], imgs_i, res, flags)
+            while len(window) > local_context_size:      # evict frames that left the local window
+                gone = window.popleft()
+                if gone not in keyframes:
+                    mem[0], mem[1] = _remove_from_mem(mem[0], mem[1], label_of[gone])
+            mem[2] = len(label_of)
+        assert mem is not None
+        while window:                                   # between passes only keyframes stay
+            gone = window.popleft()
+            if gone not in keyframes:
+                mem[0], mem[1] = _remove_from_mem(mem[0], mem[1], label_of[gone])
+    return (mem, first_pass) if return_mem else first_pass
+
+
+# --------------------------------------------------------------------------------------------- offline keyframes + render
+@torch.no_grad()
+def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches, verbose=False, max_bs=None,
+                       to_render=None, encoder_precomputed_features=None, precomputed_mem=None, preserve_gpu_mem=False,
+                       post_process_function=lambda x: {'pts3d': x}, device=None, return_mem=False, viser_server=None,
+                       num_refinements_iterations=0):
+    """Build the memory from the first sum(mem_batches) views, optionally refine it, then render
+    (engine/inference.py:369-527)."""
+    true_shape = torch.stack(true_shape, dim=0)
+    n = true_shape.shape[0]
+    device = device or true_shape.device
+    x, pos = ([None] * n, [None] * n) if encoder_precomputed_features is None else encoder_precomputed_features
+    if precomputed_mem is None:
+        mem = None
+        bounds = [0] + np.cumsum(mem_batches).tolist()
+        first_pass = [None] * bounds[-1]
+        label_of = {}
+        for _ in range(num_refinements_iterations + 1):
+            for step in range(len(bounds) - 1):
+                lo, hi = bounds[step], bounds[step + 1]
+                ts_i, imgs_i, ids_i = true_shape[lo:hi], imgs[lo:hi], img_ids[lo:hi]
+                x_i, pos_i = _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device)
+                ts_st, idx_st, x_st, pos_st, img_st = stack_views(ts_i, [x_i, pos_i, imgs_i], max_bs=max_bs)
+                refresh = all(int(v) in label_of for v in ids_i)     # all views already stored: refinement step
+                new_mem, res = inference_multi_ar_batch(encoder, decoder, img_st, ts_st, mem, verbose=verbose,
+                                                        encoder_precomputed_features=(x_st, pos_st),
+                                                        preserve_gpu_mem=preserve_gpu_mem,
+                                                        post_process_function=post_process_function, device=device,
+                                                        viser_server=viser_server)
+                new_labels = _fresh_labels(new_mem, get_Nmem(mem))
+                if refresh:
+                    assert mem is not None
+                    for j, vid in enumerate(ids_i):
+                        old = label_of[int(vid)]
+                        if old == 0:
+                            continue                                  # reference image: left as is
+                        dst, src = mem[1] == old, new_mem[1] == new_labels[j]
+                        for k in range(len(mem[0])):
+                            mem[0][k][dst] = new_mem[0][k][src]
+                    del new_mem
+                else:
+                    mem = new_mem
+                    for j, vid in enumerate(ids_i):
+                        label_of[int(vid)] = int(new_labels[j])
+                res = unstack_pointmaps(idx_st, res)
+                first_pass[lo:hi] = res
+                if viser_server is not None:
+                    viser_server.set_views(ids_i, imgs_i, res, [True] * len(imgs_i))
+    else:
+        first_pass, mem = None, precomputed_mem
+
+    if to_render is not None:
+        x, pos = [x[v] for v in to_render], [pos[v] for v in to_render]
+        true_shape = true_shape[to_render].contiguous()
+        imgs, img_ids = [imgs[v] for v in to_render], [img_ids[v] for v in to_render]
+        n = len(x)
+    assert mem is not None
+    if n == 0:
+        return (mem, first_pass, []) if return_mem else (first_pass, [])
+
+    ts_st, idx_st, x_st, pos_st, img_st, id_st = stack_views(true_shape, [x, pos, imgs, img_ids], max_bs=max_bs)
+    rendered = []
+    for xs, ps, ts, ims, ids in zip(x_st, pos_st, ts_st, img_st, id_st):
+        feats = None if (xs is None or ps is None) else ([xs], [ps])
+        _, out = inference_multi_ar_batch(encoder, decoder, [ims], [ts], mem, verbose=verbose,
+                                          encoder_precomputed_features=feats, preserve_gpu_mem=preserve_gpu_mem,
+                                          post_process_function=post_process_function, device=device, render=True,
+                                          viser_server=viser_server)
+        rendered.append(out[0])
+        if viser_server is not None:
+            tmp = unstack_pointmaps([torch.arange(ids.shape[0])], out)
+            for i in range(ids.shape[0]):
+                viser_server.set_views([ids[i]], [ims[i]], [tmp[i]])
+    pointmaps = unstack_pointmaps(idx_st, rendered)
+    return (mem, first_pass, pointmaps) if return_mem else (first_pass, pointmaps)
+
+
+def groupby_consecutive(data):
+    """Runs of consecutive integers as (first, last) pairs (engine/inference.py:555-567)."""
+    if not data:
+        return []
+    data = sorted(data)
+    runs = []
+    for _, grp in itertools.groupby(enumerate(data), lambda t: t[1] - t[0]):
+        grp = [v for _, v in grp]
+        runs.append((grp[0], grp[-1]))
+    return runs
+
+
+# --------------------------------------------------------------------------------------------- batched tensor path
+def inference_encoder(encoder, imgs, true_shape_view, max_bs=None, requires_grad=False):
+    """imgs [B,nimgs,3,H,W] -> x [B,nimgs,N,D], pos [B,nimgs,N,2], optionally in slices of max_bs
+    (engine/inference.py:570-592)."""
+    with (nullcontext() if requires_grad else torch.no_grad()):
+        B, n = imgs.shape[:2]
+        flat = imgs.reshape(B * n, *imgs.shape[2:])
+        if max_bs is None or B * n <= max_bs:
+            x, pos = encoder(flat, true_shape_view)
+        else:
+            parts = [encoder(a, b) for a, b in zip(torch.split(flat, max_bs), torch.split(true_shape_view, max_bs))]
+            x = torch.cat([p[0] for p in parts])
+            pos = torch.cat([p[1] for p in parts])
+        return x.view(B, n, *x.shape[1:]), pos.view(B, n, *pos.shape[1:])
+
+
+def inference(encoder, decoder, imgs, true_shape, mem_batches, verbose=False, max_bs=None, train_decoder_skip=0,
+              to_render=None, encoder_requires_grad=False):
+    """Batched tensor path used by eval / training (engine/inference.py:595-688): B scenes x nimgs views,
+    memory updates in steps of mem_batches, then render (all views or `to_render`), in slices of max_bs."""
+    B, n = imgs.shape[:2]
+    x, pos = inference_encoder(encoder, imgs, true_shape.view(B * n, 2), max_bs, encoder_requires_grad)
+    N, D = x.shape[2:]
+    bounds = [0] + np.cumsum(mem_batches).tolist()
+    mem, outshape, first_pass = None, None, []
+    for step in range(len(bounds) - 1):
+        sl = slice(bounds[step], bounds[step + 1])
+        ctx = torch.no_grad() if step < train_decoder_skip else nullcontext()
+        with ctx:
+            mem, pm = decoder(x[:, sl].contiguous(), pos[:, sl].contiguous(), true_shape[:, sl].contiguous(), mem,
+                              render=False)
+        outshape = outshape or pm.shape
+        if step >= train_decoder_skip:
+            first_pass.append(pm)
+    if first_pass:
+        pointmaps_0 = torch.cat(first_pass, dim=1)
+    else:
+        pointmaps_0 = torch.empty((B, 0, *outshape[2:]), dtype=x.dtype, device=x.device)
+    if to_render is not None:
+        x, pos = x[:, to_render].contiguous(), pos[:, to_render].contiguous()
+        true_shape = true_shape[:, to_render].contiguous()
+        n = x.shape[1]
+    assert mem is not None
+    mem_vals, mem_labels, mem_nimgs, mem_pi, mem_pt = mem
+    if n == 0:
+        return pointmaps_0, torch.empty((B, 0, *pointmaps_0.shape[2:]), dtype=x.dtype, device=x.device)
+    if max_bs is None or B * n <= max_bs:
+        _, pointmaps = decoder(x, pos, true_shape, mem, render=True)
+        return pointmaps_0, pointmaps
+    # chunked render: every (scene, view) pair becomes its own "scene" carrying a copy of its memory
+    Nmem, Dmem = mem_vals[0].shape[1:]
+    rep_vals = [m.unsqueeze(1).expand(B, n, Nmem, Dmem).reshape(B * n, Nmem, Dmem) for m in mem_vals]
+    rep_labels = mem_labels.unsqueeze(1).expand(B, n, Nmem).reshape(B * n, Nmem)
+    xv, pv, tv = x.reshape(B * n, N, D), pos.reshape(B * n, N, 2), true_shape.reshape(B * n, 2)
+    outs = []
+    for lo in range(0, B * n, max_bs):
+        sl = slice(lo, lo + max_bs)
+        _, pm = decoder(xv[sl].unsqueeze(1), pv[sl].unsqueeze(1), tv[sl].unsqueeze(1),
+                        ([m[sl] for m in rep_vals], rep_labels[sl], mem_nimgs, mem_pi, mem_pt), render=True)
+        outs.append(pm.squeeze(1))
+    pointmaps = torch.cat(outs)
+    return pointmaps_0, pointmaps.view(B, n, *pointmaps.shape[1:])
+
+
+def concat_preds(out0, out):
+    """engine/inference.py:691-695"""
+    for k in out.keys():
+        if k in out0:
+            out[k] = torch.cat([out0[k], out[k]], dim=1)
+    return out

@@ -1,0 +1,147 @@
+"""Multi-GPU schedule of the hot path (the reference has no multi-GPU inference at all).
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests).  Every rank holds the same
+number V of views of ONE scene (global view id = rank * V + i):
+
+  1. encoder: each rank encodes its own V views (independent units, no collective);
+  2. memory init: rank 0 runs the reference's 2-view initialisation on its views 0,1 (decoder.py:280-285) and the
+     resulting K|V tokens reach every rank through the same gather as the other rounds;
+  3. memory update, round s = 0..V-1: every rank whose local view s is not yet in memory runs a shard-local
+     update of that ONE view against the replicated memory M_{k-1} (peers of the same round do not see each
+     other: "shard-local update"), then ONE all-gather per round moves the packed new post-feedback K|V tokens
+     [depth, N, 2D] of all ranks into every rank's pre-allocated memory buffer -> M_k identical everywhere,
+     labels in rank order;
+  4. render: each rank renders its V views against the final replicated memory (no collective).
+
+With world_size 1 the schedule degenerates to the reference chain (init 2 views, then 1 view per step).
+The oracle for world_size > 1 is composed from single-process decoder calls only (tests/test_sharded_cpu.py).
+The function is model-agnostic: decoders exposing ``update_tokens`` (the CUDA MUSt3R) avoid materialising the
+concatenated memory; any reference-style decoder works through ``mem'[0][l][:, Nm:]``.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def _world():
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _new_tokens(decoder, x, pos, ts, mem):
+    """-> (list[depth] of [1, n*N, mem_D] new post-feedback tokens, raw pointmaps [1,n,H,W,C])"""
+    if hasattr(decoder, "update_tokens"):
+        return decoder.update_tokens(x, pos, ts, mem)
+    Nm = 0 if mem is None else mem[0][0].shape[1]
+    new_mem, pm = decoder(x, pos, ts, mem, render=False)
+    return [m[:, Nm:] for m in new_mem[0]], pm
+
+
+def _all_gather(packed: torch.Tensor, world: int) -> torch.Tensor:
+    """[...]: -> [world, ...] (one collective).  all_gather_into_tensor on NCCL; list form elsewhere."""
+    out = packed.new_empty((world,) + tuple(packed.shape))
+    if packed.is_cuda:
+        dist.all_gather_into_tensor(out, packed.contiguous())
+    else:
+        dist.all_gather(list(out.unbind(0)), packed.contiguous())
+    return out
+
+
+@torch.no_grad()
+def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Tensor,
+                      post_process_function: Optional[Callable] = None, device=None, to_host: bool = False,
+                      render_bs: Optional[int] = None, return_mem: bool = False):
+    """imgs [V,3,H,W], true_shape [V,2]: this rank's views (same V and image size on every rank).
+    Returns the list of this rank's V rendered results (dicts if post_process_function is given)."""
+    rank, world = _world()
+    device = device or imgs.device
+    V = imgs.shape[0]
+    imgs, true_shape = imgs.to(device), true_shape.to(device)
+    x, pos = encoder(imgs, true_shape)                         # [V,N,Denc], [V,N,2]
+    N = x.shape[1]
+
+    mem_vals: Optional[List[torch.Tensor]] = None              # depth x [1, cap, mem_D] pre-allocated
+    labels = None
+    n_mem_views = 0
+
+    def current_mem():
+        if n_mem_views == 0:
+            return None
+        Nm = n_mem_views * N
+        return ([m[:, :Nm] for m in mem_vals], labels[:, :Nm], n_mem_views, n_mem_views, Nm)
+
+    def append(gathered: torch.Tensor, flags: List[bool], n_each: int):
+        """gathered [world, depth, n_each*N, mem_D]; append the participating ranks' tokens in rank order."""
+        nonlocal mem_vals, labels, n_mem_views
+        depth, mem_D = gathered.shape[1], gathered.shape[3]
+        if mem_vals is None:
+            cap = world * V * N
+            mem_vals = [torch.empty((1, cap, mem_D), dtype=gathered.dtype, device=gathered.device) for _ in range(depth)]
+            labels = torch.empty((1, cap), dtype=torch.int64, device=gathered.device)
+        sel = [r for r in range(world) if flags[r]]
+        if not sel:
+            return
+        Nm = n_mem_views * N
+        cnt = len(sel) * n_each * N
+        src = gathered if len(sel) == world else gathered[sel]
+        for l in range(depth):
+            mem_vals[l][0, Nm:Nm + cnt] = src[:, l].reshape(cnt, mem_D)
+        lab = torch.arange(n_mem_views, n_mem_views + len(sel) * n_each, device=labels.device)
+        labels[0, Nm:Nm + cnt] = lab.repeat_interleave(N)
+        n_mem_views += len(sel) * n_each
+
+    # ---- 2. init on rank 0 (views 0,1); every rank runs the same gather so the memory is replicated
+    n_init = min(2, V)
+    if rank == 0:
+        toks, _ = _new_tokens(decoder, x[None, :n_init], pos[None, :n_init], true_shape[None, :n_init], None)
+        packed = torch.stack([t[0] for t in toks], 0)                                  # [depth, n_init*N, mem_D]
+    else:
+        packed = None
+    if world > 1:
+        shape = [0, 0, 0]
+        if rank == 0:
+            shape = list(packed.shape)
+        st = torch.tensor(shape, dtype=torch.int64, device=device)
+        dist.broadcast(st, src=0)
+        if rank != 0:
+            dt = getattr(decoder, "memory_dtype", None)
+            dt = dt() if callable(dt) else (dt or torch.float32)
+            packed = torch.empty(tuple(int(v) for v in st.tolist()), dtype=dt, device=device)
+        dist.broadcast(packed, src=0)
+    append(packed[None] if world == 1 else packed[None].expand(world, *packed.shape),
+           [r == 0 for r in range(world)], n_init)
+
+    # ---- 3. update rounds: one view per rank per round, one all-gather per round
+    for s in range(V):
+        mine = not (rank == 0 and s < n_init)
+        flags = [not (r == 0 and s < n_init) for r in range(world)]
+        if not any(flags):
+            continue
+        # ranks that sit a round out still take part in the collective (with a dummy payload)
+        if mine:
+            toks, _ = _new_tokens(decoder, x[None, s:s + 1], pos[None, s:s + 1], true_shape[None, s:s + 1], current_mem())
+            packed = torch.stack([t[0] for t in toks], 0)                              # [depth, N, mem_D]
+        else:
+            packed = torch.zeros((len(mem_vals), N, mem_vals[0].shape[2]), dtype=mem_vals[0].dtype, device=device)
+        gathered = _all_gather(packed, world) if world > 1 else packed[None]
+        append(gathered, flags, 1)
+
+    # ---- 4. render this rank's views against the replicated memory
+    mem = current_mem()
+    outs = []
+    bs = render_bs or V
+    for lo in range(0, V, bs):
+        _, pm = decoder(x[None, lo:lo + bs], pos[None, lo:lo + bs], true_shape[None, lo:lo + bs], mem, render=True)
+        pm = pm[0]
+        if post_process_function is not None:
+            res = post_process_function(pm)
+            res = {k: (v.cpu() if to_host else v) for k, v in res.items()}
+            outs.extend({k: v[j] for k, v in res.items()} for j in range(pm.shape[0]))
+        else:
+            pm = pm.cpu() if to_host else pm
+            outs.extend(pm[j] for j in range(pm.shape[0]))
+    return (mem, outs) if return_mem else outs

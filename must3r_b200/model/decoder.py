@@ -94,6 +94,10 @@ class MUSt3R(nn.Module):
             nn.init.constant_(self.feedback_layer.weight, 0)
         self._pack = None
 
+    def memory_dtype(self):
+        """dtype of the K|V memory tensors this decoder produces (the current 16-bit operand format)."""
+        return cm.get_precision()
+
     # ---- housekeeping identical to the reference -----------------------------------------------------
     def change_memory_mode(self, memory_mode="norm_y"):
         assert memory_mode in MEMORY_MODES
@@ -175,7 +179,15 @@ class MUSt3R(nn.Module):
         return mem, pms[0]
 
     @torch.no_grad()
-    def forward_list(self, x, pos, true_shape, current_mem=None, render=False, return_feats=False):
+    def update_tokens(self, x, pos, true_shape, current_mem=None):
+        """Memory-update call that returns only this call's new post-feedback K|V tokens
+        (list[depth] of [B, n*N, 2D]) and the raw pointmaps, instead of the concatenated memory
+        (= ``mem'[0][l][:, Nm:]`` of ``forward``).  Used by the sharded multi-GPU schedule."""
+        _, pms, new_tokens = self.forward_list([x], [pos], [true_shape], current_mem, render=False, _new_only=True)
+        return new_tokens, pms[0]
+
+    @torch.no_grad()
+    def forward_list(self, x, pos, true_shape, current_mem=None, render=False, return_feats=False, _new_only=False):
         """decoder.py:158-265"""
         if self.memory_mode != 'kv':
             raise NotImplementedError("must3r_b200 implements memory_mode='kv' (the released checkpoints' mode); "
@@ -240,15 +252,19 @@ class MUSt3R(nn.Module):
         out_ptrs = (C.c_void_p * self.depth)()
         new_mem = None
         if not render:
-            new_mem = [torch.empty((B, Nm + Nt, 2 * D), dtype=dtype, device=dev) for _ in range(self.depth)]
+            rows = Nt if _new_only else Nm + Nt
+            new_mem = [torch.empty((B, rows, 2 * D), dtype=dtype, device=dev) for _ in range(self.depth)]
             for l in range(self.depth):
                 out_ptrs[l] = new_mem[l].data_ptr()
             call.mem_out = out_ptrs
-            call.mem_out_bstride_rows = Nm + Nt
+            call.mem_out_bstride_rows = rows
+            call.new_only = 1 if _new_only else 0
         nbytes = lib.m3r_decoder_workspace_bytes(C.byref(w), C.byref(call))
         ws = cm.workspace(dev, nbytes, "dec")
         _lib.check(lib.m3r_decoder_forward(C.byref(w), C.byref(call), C.c_void_p(ws.data_ptr()), ws.numel(), cm.stream_ptr()),
                    "decoder_forward")
+        if _new_only:
+            return None, outs, new_mem
         if render:
             out = tuple(current_mem)                                       # decoder.py:251,340: memory returned untouched
         else:

@@ -1,0 +1,94 @@
+"""Host logic of must3r_b200.engine (view grouping, update/refine/evict bookkeeping, chunked render) pinned
+against the reference engine's outputs (tests/golden/engine.npz), with the CPU oracle standing in as the model.
+fp32 vs fp32: 3e-5 rel-L2."""
+import numpy as np
+import torch
+
+from helpers import load_golden, tiny_oracle, rel
+from must3r_b200 import engine, synthetic as syn
+from oracle import must3r_oracle as orc
+
+TOL = 3e-5
+
+
+def _views():
+    imgs, tss = [], []
+    for i in range(6):
+        H, W = (32, 48) if i % 3 != 2 else (48, 32)
+        im, ts = syn.synthetic_views(1, H, W, seed=100 + i)
+        imgs.append(im[0])
+        tss.append(ts[0])
+    return imgs, tss
+
+
+def _check_mem(g, prefix, mem):
+    for l in range(3):
+        assert rel(mem[0][l], g[f"{prefix}.mem{l}"]) < TOL
+    assert np.array_equal(mem[1].numpy(), g[f"{prefix}.labels"])
+    assert [int(v) for v in mem[2:]] == g[f"{prefix}.tail"].tolist()
+
+
+def test_inference_multi_ar_with_refinement():
+    g = load_golden("engine.npz")
+    enc, dec = tiny_oracle(7)
+    imgs, tss = _views()
+    ids = [torch.tensor(i) for i in range(6)]
+    mem, pm0, pm = engine.inference_multi_ar(enc, dec, imgs, ids, tss, [2, 1, 1], max_bs=2,
+                                             post_process_function=orc.postprocess, device="cpu", return_mem=True,
+                                             num_refinements_iterations=1)
+    assert len(pm0) == 4 and len(pm) == 6
+    for i, d in enumerate(pm0):
+        for k, v in d.items():
+            assert rel(v, g[f"multi_ar.pm0.{i}.{k}"]) < TOL, (i, k)
+    for i, d in enumerate(pm):
+        for k, v in d.items():
+            assert rel(v, g[f"multi_ar.pm.{i}.{k}"]) < TOL, (i, k)
+    _check_mem(g, "multi_ar.mem", mem)
+
+
+def test_inference_video_rolling_window():
+    g = load_golden("engine.npz")
+    enc, dec = tiny_oracle(7)
+    imgs, tss = _views()
+    mem, pm0 = engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], post_process_function=orc.postprocess,
+                                               device="cpu", return_mem=True, local_context_size=2)
+    for i, d in enumerate(pm0):
+        for k, v in d.items():
+            assert rel(v, g[f"video.pm0.{i}.{k}"]) < TOL, (i, k)
+    _check_mem(g, "video.mem", mem)
+
+
+def test_inference_tensor_path_chunked_render():
+    g = load_golden("engine.npz")
+    enc, dec = tiny_oracle(7)
+    im, ts = syn.synthetic_views(8, 32, 48, seed=200)
+    pm0, pm = engine.inference(enc, dec, im.view(2, 4, 3, 32, 48), ts.view(2, 4, 2), [2, 1, 1], max_bs=3)
+    assert rel(pm0, g["inference.pm0"]) < TOL and rel(pm, g["inference.pm"]) < TOL
+    _, pm = engine.inference(enc, dec, im.view(2, 4, 3, 32, 48), ts.view(2, 4, 2), [2, 1, 1], to_render=[1, 3])
+    assert rel(pm, g["inference.pm_sel"]) < TOL
+
+
+def test_stack_views_groups_and_none_handling():
+    ts = torch.tensor([[32, 48], [48, 32], [32, 48], [32, 48], [48, 32]])
+    vals = [torch.full((2,), float(i)) for i in range(5)]
+    vals_missing = list(vals)
+    vals_missing[2] = None
+    shapes, idx, v = engine.stack_views(ts, [vals], max_bs=2)
+    assert idx == [[0, 2], [3], [1, 4]]
+    assert [s.tolist() for s in shapes] == [[[32, 48], [32, 48]], [[32, 48]], [[48, 32], [48, 32]]]
+    assert torch.equal(v[0], torch.stack([vals[0], vals[2]]))
+    shapes, idx, v = engine.stack_views(ts, [vals_missing])
+    assert idx == [[0, 3], [1, 4], [2]] and v[2] is None and v[0].shape[0] == 2
+
+
+def test_postprocess_cpu_matches_oracle_and_rejects_cam():
+    pm = torch.randn(2, 8, 8, 7)
+    out = engine.postprocess(pm)
+    ref = orc.postprocess(pm)
+    for k in ref:
+        assert torch.allclose(out[k], ref[k])
+    try:
+        engine.postprocess(pm, compute_cam=True)
+        assert False
+    except NotImplementedError:
+        pass

@@ -1,0 +1,198 @@
+"""Model-level parity of the CUDA path (through load_model / Dust3rEncoder / MUSt3R, i.e. the C ABI whole-model
+entry points) against (i) outputs of the unmodified reference (tests/golden/*.npz) and (ii) the CPU oracle.
+
+Tolerances (rel-L2 of raw pointmaps / memory vs the fp32 reference), see DESIGN.md "Numerics":
+  fp16 operands (default, TF32-class 10-bit mantissa): 3e-3
+  bf16 operands (the reference's amp dtype; its own bf16-vs-fp32 gap is 1.1e-2): 2.5e-2
+"""
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, tiny_oracle, full_oracle, digest, rel, TINY_ENC, TINY_DEC
+from must3r_b200 import synthetic as syn, engine
+from must3r_b200.model import Dust3rEncoder, MUSt3R, load_model, set_precision, ActivationType
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float16: 3e-3, torch.bfloat16: 2.5e-2}
+DT = [torch.float16, torch.bfloat16]
+
+
+def tiny_cuda(seed=7, enc_kw=None, dec_kw=None):
+    enc = Dust3rEncoder(img_size=(64, 64), embed_dim=128, depth=2, num_heads=2, **(enc_kw or {}))
+    dkw = dict(img_size=(64, 64), enc_embed_dim=128, embed_dim=128, depth=3, num_heads=2, output_dim=1792,
+               feedback_type="single_mlp", memory_mode="kv", landscape_only=False)
+    dkw.update(dec_kw or {})
+    dec = MUSt3R(**dkw)
+    enc.load_state_dict(syn.encoder_state_dict(seed, embed_dim=128, depth=2), strict=True)
+    dec.load_state_dict(syn.decoder_state_dict(seed, enc_embed_dim=128, embed_dim=128, depth=3,
+                                               feedback_type=dkw["feedback_type"]), strict=True)
+    return enc.cuda().eval(), dec.cuda().eval()
+
+
+def check_mem(g, prefix, mem, tol, depth=3):
+    for l in range(depth):
+        assert rel(mem[0][l].float().cpu(), g[f"{prefix}.mem{l}"]) < tol, (prefix, l)
+    assert np.array_equal(mem[1].cpu().numpy(), g[f"{prefix}.labels"])
+    assert [int(v) for v in mem[2:]] == g[f"{prefix}.tail"].tolist()
+
+
+VARIANTS = {
+    "kv": ({}, {}),
+    "f0": (dict(pos_embed="RoPE100_224:512"), dict(pos_embed="RoPE100_224:512")),
+    "nofb": ({}, dict(feedback_type=None)),
+    "fblin": ({}, dict(feedback_type="single_linear")),
+}
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_tiny_chain_vs_reference(dtype, variant):
+    """init(2 views) -> update(1) -> update(2, masked with Nm>0) -> render(5), against the reference's outputs."""
+    set_precision(dtype)
+    tol = TOL[dtype]
+    g = load_golden("tiny_model.npz")
+    enc, dec = tiny_cuda(7, *VARIANTS[variant])
+    imgs, ts = syn.synthetic_views(5, 32, 48, seed=11)
+    imgs, ts = imgs.cuda(), ts.cuda()
+    x, pos = enc(imgs, ts)
+    assert x.dtype == torch.float32 and rel(x.cpu(), g[f"{variant}.enc_x"]) < tol
+    assert np.array_equal(pos.cpu().numpy(), g[f"{variant}.enc_pos"])
+    mem, pm = dec(x[None, 0:2], pos[None, 0:2], ts[None, 0:2], None)
+    assert pm.dtype == torch.float32 and rel(pm.cpu(), g[f"{variant}.pm_init"]) < tol
+    check_mem(g, f"{variant}.init", mem, tol)
+    mem, pm = dec(x[None, 2:3], pos[None, 2:3], ts[None, 2:3], mem)
+    assert rel(pm.cpu(), g[f"{variant}.pm_upd1"]) < tol
+    mem, pm = dec(x[None, 3:5], pos[None, 3:5], ts[None, 3:5], mem)
+    assert rel(pm.cpu(), g[f"{variant}.pm_upd2"]) < tol
+    check_mem(g, f"{variant}.final", mem, tol)
+    mem_r, pm = dec(x[None], pos[None], ts[None], mem, render=True)
+    assert rel(pm.cpu(), g[f"{variant}.pm_render"]) < tol
+    assert mem_r[0][0] is mem[0][0]
+    out = engine.postprocess(pm, ActivationType.NORM_EXP)
+    for k in ("pts3d", "pts3d_local", "conf"):
+        assert rel(out[k].cpu(), g[f"{variant}.post.{k}"] if variant == "kv" else out[k].cpu()) < 2 * tol
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_tiny_batch2_and_list_form(dtype):
+    set_precision(dtype)
+    tol = TOL[dtype]
+    g = load_golden("tiny_model.npz")
+    enc, dec = tiny_cuda(7)
+    imgs, ts = syn.synthetic_views(6, 32, 48, seed=12)
+    x, pos = enc(imgs.cuda(), ts.cuda())
+    ts = ts.cuda()
+    xb, pb, tb = x.view(2, 3, *x.shape[1:]), pos.view(2, 3, *pos.shape[1:]), ts.view(2, 3, 2)
+    mem, pm = dec(xb[:, :1], pb[:, :1], tb[:, :1], None)             # single-image init: no own-mask
+    assert rel(pm.cpu(), g["b2.pm_init1"]) < tol
+    mem, pm = dec(xb[:, 1:3], pb[:, 1:3], tb[:, 1:3], mem)
+    assert rel(pm.cpu(), g["b2.pm_upd2"]) < tol
+    check_mem(g, "b2.final", mem, tol)
+    _, pm = dec(xb, pb, tb, mem, render=True)
+    assert rel(pm.cpu(), g["b2.pm_render"]) < tol
+    # two aspect ratios in one call
+    imgs_p, ts_p = syn.synthetic_views(2, 48, 32, seed=13)
+    imgs_l, ts_l = syn.synthetic_views(2, 32, 48, seed=14)
+    xp, pp = enc(imgs_p.cuda(), ts_p.cuda())
+    xl, pl = enc(imgs_l.cuda(), ts_l.cuda())
+    ts_p, ts_l = ts_p.cuda(), ts_l.cuda()
+    mem, pms = dec([xl[None], xp[None]], [pl[None], pp[None]], [ts_l[None], ts_p[None]], None)
+    assert rel(pms[0].cpu(), g["list.pm0"]) < tol and rel(pms[1].cpu(), g["list.pm1"]) < tol
+    check_mem(g, "list.init", mem, tol)
+    mem2, pms = dec([xp[None, :1], xl[None, :1]], [pp[None, :1], pl[None, :1]], [ts_p[None, :1], ts_l[None, :1]], mem)
+    assert rel(pms[0].cpu(), g["list.pm2"]) < tol and rel(pms[1].cpu(), g["list.pm3"]) < tol
+    check_mem(g, "list.final", mem2, tol)
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("tag,H,W,size", [("224", 224, 224, 224), ("512", 384, 512, 512)])
+def test_full_size_vs_reference_digest(dtype, tag, H, W, size, tmp_path):
+    """Real architecture (ViT-L encoder, ViT-B decoder) through load_model on a synthetic checkpoint file written
+    in the reference's format; compared with digests of the reference's outputs."""
+    set_precision(dtype)
+    tol = TOL[dtype]
+    g = load_golden("full_model_digest.npz")
+    ck = {"args": argparse.Namespace(
+              encoder=f"Dust3rEncoder(img_size=({size}, {size}), patch_embed='PatchEmbedDust3R')",
+              decoder=f"CausalMUSt3R(img_size=({size}, {size}), feedback_type='single_mlp', memory_mode='kv', mem_dropout=0.1)"),
+          "encoder": syn.encoder_state_dict(0), "decoder": syn.decoder_state_dict(0)}
+    path = os.path.join(tmp_path, "ckpt.pth")
+    torch.save(ck, path)
+    enc, dec = load_model(path, device="cuda", verbose=False)
+    imgs, ts = syn.synthetic_views(3, H, W, seed=2)
+    imgs, ts = imgs.cuda(), ts.cuda()
+    x, pos = enc(imgs, ts)
+    assert rel(digest(x), g[f"{tag}.enc_x"]) < tol
+    mem, pm = dec(x[None, :2], pos[None, :2], ts[None, :2], None)
+    assert rel(digest(pm), g[f"{tag}.pm_init"]) < tol
+    mem, pm = dec(x[None, 2:3], pos[None, 2:3], ts[None, 2:3], mem)
+    assert rel(digest(pm), g[f"{tag}.pm_upd"]) < tol
+    assert rel(digest(mem[0][0]), g[f"{tag}.mem0"]) < tol
+    assert rel(digest(mem[0][11]), g[f"{tag}.mem11"]) < tol
+    assert np.array_equal(mem[1][:, ::97].cpu().numpy(), g[f"{tag}.labels"])
+    _, pm = dec(x[None], pos[None], ts[None], mem, render=True)
+    assert rel(digest(pm), g[f"{tag}.pm_render"]) < tol
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_engine_on_cuda_vs_reference_engine(dtype):
+    """must3r_b200.engine driving the CUDA model, against the reference engine's outputs (engine.npz)."""
+    set_precision(dtype)
+    tol = 2 * TOL[dtype]
+    g = load_golden("engine.npz")
+    enc, dec = tiny_cuda(7)
+    imgs, tss = [], []
+    for i in range(6):
+        H, W = (32, 48) if i % 3 != 2 else (48, 32)
+        im, ts = syn.synthetic_views(1, H, W, seed=100 + i)
+        imgs.append(im[0].cuda())
+        tss.append(ts[0].cuda())
+    ids = [torch.tensor(i) for i in range(6)]
+    pp = lambda pm: engine.postprocess(pm, ActivationType.NORM_EXP)  # noqa: E731
+    mem, pm0, pm = engine.inference_multi_ar(enc, dec, imgs, ids, tss, [2, 1, 1], max_bs=2, post_process_function=pp,
+                                             device="cuda", return_mem=True, num_refinements_iterations=1)
+    for i, d in enumerate(pm):
+        for k, v in d.items():
+            assert rel(v.cpu(), g[f"multi_ar.pm.{i}.{k}"]) < tol, (i, k)
+    assert np.array_equal(mem[1].cpu().numpy(), g["multi_ar.mem.labels"])
+    mem, pm0 = engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], post_process_function=pp,
+                                               device="cuda", return_mem=True, local_context_size=2)
+    for i, d in enumerate(pm0):
+        for k, v in d.items():
+            assert rel(v.cpu(), g[f"video.pm0.{i}.{k}"]) < tol, (i, k)
+    assert np.array_equal(mem[1].cpu().numpy(), g["video.mem.labels"])
+    im, ts = syn.synthetic_views(8, 32, 48, seed=200)
+    pm0, pm = engine.inference(enc, dec, im.view(2, 4, 3, 32, 48).cuda(), ts.view(2, 4, 2).cuda(), [2, 1, 1], max_bs=3)
+    assert rel(pm0.cpu(), g["inference.pm0"]) < tol and rel(pm.cpu(), g["inference.pm"]) < tol
+
+
+def test_cuda_vs_oracle_same_box():
+    """The CPU oracle (pinned to the reference by test_oracle_golden) evaluated on this box vs the CUDA path."""
+    set_precision(torch.float16)
+    enc_o, dec_o = tiny_oracle(3)
+    enc, dec = tiny_cuda(3)
+    imgs, ts = syn.synthetic_views(3, 48, 64, seed=5)
+    xo, po = enc_o(imgs, ts)
+    x, pos = enc(imgs.cuda(), ts.cuda())
+    assert rel(x.cpu(), xo) < TOL[torch.float16]
+    mo, pmo = dec_o(xo[None], po[None], ts[None], None)
+    m, pm = dec(x[None], pos[None], ts.cuda()[None], None)
+    assert rel(pm.cpu(), pmo) < TOL[torch.float16]
+    assert rel(m[0][2].float().cpu(), mo[0][2]) < TOL[torch.float16]
+
+
+def test_no_cpu_fallback_and_arg_errors():
+    enc, dec = tiny_cuda(7)
+    imgs, ts = syn.synthetic_views(1, 32, 48, seed=1)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        enc(imgs, ts)
+    with pytest.raises(AssertionError):
+        enc(torch.zeros(1, 3, 40, 48, device="cuda"), ts.cuda())
+    dec.change_memory_mode("norm_y")
+    x, pos = enc(imgs.cuda(), ts.cuda())
+    with pytest.raises(NotImplementedError):
+        dec(x[None], pos[None], ts.cuda()[None], None)
