@@ -41,6 +41,18 @@ def flops_per_job(V, mem_views_schedule):
     return enc + upd + ren
 
 
+def effective_cores():
+    """Host threads this process may actually use: min(sched affinity, cgroup cpu quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:  # noqa: BLE001
+        pass
+    return max(1, min(n, 64))          # torch CPU GEMMs stop scaling (and start thrashing) far below 128 threads
+
+
 class ClockSampler:
     def __init__(self, device_index):
         self.idx, self.rows, self._stop = device_index, [], threading.Event()
@@ -101,7 +113,7 @@ def cpu_reference_job(n_views, threads):
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = effective_cores()
     n = args.cpu_views
     job = cpu_reference_job(n, threads)
     for _ in range(args.warmup):
@@ -261,7 +273,7 @@ def main():
     # ---- CPU baseline on the host cores (rank 0, N=1 only), bounded sample
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
+        threads = effective_cores()
         cj = cpu_reference_job(args.cpu_views, threads)
         cj()
         t0 = time.perf_counter()

@@ -1,18 +1,25 @@
 // FlashAttention-style softmax(Q K^T * scale) V for head_dim 64 on sm_100a tensor cores (tcgen05 + TMEM).
 //
-// One CTA = one (batch, head, 128-query tile); two CTAs are co-resident per SM (80 KB smem, 256 TMEM
-// columns each) so that one CTA's softmax overlaps the other's MMAs.
-//   warp 0     : TMA producer -- Q once, then K and V tiles (128 keys x 64) through 2-deep mbarrier rings
-//   warp 1     : TMEM allocator + single-thread MMA issuer:  S = Q K^T (SS form), O_tile = P V (A = P from TMEM,
-//                B = V as an MN-major smem operand, so V is consumed in its natural [keys, d] layout)
-//   warps 2..5 : softmax -- one query row per thread (TMEM lane == row, no shuffles needed), two passes over
-//                S in TMEM (row max, then exp2 / row sum / pack P), online-softmax state (m, l) and the output
-//                accumulator O[64] in registers.
-// TMEM buffer b (128 columns) holds S_b; after the softmax has consumed it, P_b overwrites columns [0,64)
-// (packed 16-bit pairs) and the P V product lands in columns [64,128).
+// One CTA = one (batch, head, QT x 128 queries [, key split]).  QT = 2 for throughput shapes: the two query tiles
+// share every K / V tile that TMA brings in (half the L2->smem traffic) and ping-pong on the tensor pipe, so one
+// tile's softmax overlaps the other's MMAs.  Roles:
+//   warps 0..4*QT-1 : softmax warpgroup per query tile -- ONE query row per thread (TMEM lane == row, so row max /
+//                     row sum need no shuffles); single pass over S held in registers: row max, exp2 with the
+//                     scale folded in, row sum, pack P to 16-bit and store it over S's own TMEM columns.
+//   warp 4*QT       : TMA producer -- Q tiles once, then K and V tiles (128 keys x 64) through mbarrier rings.
+//                     3-D tensor maps: rows beyond Nk read as zeros even inside over-allocated memory buffers.
+//   warp 4*QT+1     : TMEM allocator + single-thread MMA issuer:  S = Q K^T (both operands K-major smem),
+//                     O += P V with P as the TMEM A operand and V as an MN-major smem B operand (V is consumed in
+//                     its natural [keys, d] layout -- no transpose anywhere in the pipeline).
+// O accumulates in TMEM across key tiles.  The running max used in the exponent is only refreshed when the true
+// row max grew by more than 2^8 (lazy rescaling): the rare refresh multiplies O in TMEM by the correction factor;
+// the final O / l is mathematically unchanged.
+// TMEM columns (QT=2): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); P_x aliases S_x[0,64).
 //
-// Keys come from two segments (stored memory + this step's new tokens) so the reference's torch.cat of the
-// memory (decoder.py:306) never happens; a per-batch skip range implements make_mem_mask (decoder.py:119-139).
+// Keys come from two segments (stored memory + this step's new tokens) so the reference's torch.cat of the memory
+// (decoder.py:306) never happens; a per-batch skip range implements make_mem_mask (decoder.py:119-139): fully
+// masked key tiles are never loaded.  Small grids (one view per step) split the key range over several CTAs; a
+// combine kernel merges the partial (O, m, l).
 #include <math.h>
 #include "ptx.cuh"
 #include "m3r_internal.h"
@@ -22,20 +29,28 @@ namespace m3r {
 constexpr int AT_BM = 128;
 constexpr int AT_BN = 128;
 constexpr int HD = 64;
-constexpr int KS = 2;                        // K / V ring depth
-constexpr int AT_THREADS = 192;
 constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB
-constexpr int AT_SMEM = (1 + 2 * KS) * TILE_BYTES + 1024 + 256;
-constexpr int AT_TMEM_COLS = 256;
+constexpr float RESCALE_THRESHOLD = 8.0f;    // log2 units
+
+template <int QT> struct AttnCfg {
+  static constexpr int KS = QT == 2 ? 3 : 2;                       // K / V ring depth
+  static constexpr int THREADS = 32 * (4 * QT + 2);
+  static constexpr int SMEM = (QT + 2 * KS) * TILE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = QT == 2 ? 512 : 256;
+};
 
 struct AttnParams {
   int Nq, Nk0, Nk1;
   int kv_group;
   int skip_lo, skip_step, skip_len;
-  int is_bf16;
+  int splits;                // key-range splits (>=1); blockIdx.z = b * splits + split
   float sl2;                 // scale * log2(e)
-  void* O;
+  void* O;                   // [B*Nq, H*64] 16-bit                     (splits == 1)
   long long ldo;
+  float* part_o;             // [splits, B*Nq, H*64] fp32 unnormalised  (splits > 1)
+  float* part_ml;            // [splits, B*Nq, H, 2]  (m_used * sl2, l)
+  int H;
+  long long rows_total;      // B * Nq
 };
 
 struct TileIt {
@@ -47,16 +62,16 @@ struct TileIt {
 
 // Enumerate key tiles, skipping the ones entirely inside the skip range. Every warp role runs the same walk.
 struct TileWalk {
-  int nk[2], lo, hi;
+  int nk0, nk1, lo, hi;
   int seg, t;
-  __device__ TileWalk(int nk0, int nk1, int lo_, int hi_) : lo(lo_), hi(hi_), seg(0), t(0) { nk[0] = nk0; nk[1] = nk1; }
+  __device__ TileWalk(int nk0_, int nk1_, int lo_, int hi_) : nk0(nk0_), nk1(nk1_), lo(lo_), hi(hi_), seg(0), t(0) {}
   __device__ bool next(TileIt& it) {
     while (seg < 2) {
-      const int n = nk[seg];
+      const int n = seg == 0 ? nk0 : nk1;
       if (t * AT_BN >= n) { ++seg; t = 0; continue; }
       const int l0 = t * AT_BN;
       const int l1 = min(l0 + AT_BN, n);
-      const int base = seg == 0 ? 0 : nk[0];
+      const int base = seg == 0 ? 0 : nk0;
       const int g0 = base + l0, g1 = base + l1;
       const int cur_t = t++;
       if (g0 >= lo && g1 <= hi) continue;     // fully masked: never loaded nor multiplied
@@ -68,243 +83,350 @@ struct TileWalk {
   }
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool BF16> __device__ __forceinline__ uint32_t packp(float lo, float hi) {
+  uint32_t r;
+  if (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+template <bool BF16, int QT>
+__global__ void __launch_bounds__(AttnCfg<QT>::THREADS, 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
             const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
             const __grid_constant__ CUtensorMap tmV1, const AttnParams p) {
+  using Cfg = AttnCfg<QT>;
+  constexpr int KS = Cfg::KS;
+  constexpr int TMA_WARP = 4 * QT, MMA_WARP = 4 * QT + 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;
-  uint8_t* sV = smem + (1 + KS) * TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (1 + 2 * KS) * TILE_BYTES);
+  uint8_t* sQ = smem;                                   // QT tiles
+  uint8_t* sK = smem + QT * TILE_BYTES;                 // KS tiles
+  uint8_t* sV = smem + (QT + KS) * TILE_BYTES;          // KS tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (QT + 2 * KS) * TILE_BYTES);
   uint64_t* q_full = bars;             // [1]
   uint64_t* k_full = bars + 1;         // [KS]
   uint64_t* k_empty = k_full + KS;     // [KS]
   uint64_t* v_full = k_empty + KS;     // [KS]
   uint64_t* v_empty = v_full + KS;     // [KS]
-  uint64_t* s_full = v_empty + KS;     // [2]   MMA -> softmax : S_b ready
-  uint64_t* p_full = s_full + 2;       // [2]   softmax -> MMA : P_b stored in TMEM
-  uint64_t* o_full = p_full + 2;       // [2]   MMA -> softmax : (P V)_b ready
-  uint64_t* s_empty = o_full + 2;      // [2]   softmax -> MMA : buffer b drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_empty + 2);
+  uint64_t* s_full = v_empty + KS;     // [2]   MMA -> softmax x : S_x(j) ready
+  uint64_t* p_full = s_full + 2;       // [2]   softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
+  uint64_t* o_done = p_full + 2;       // [2]   MMA -> softmax x : P_x(j) V(j) accumulated into O_x
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qblk = blockIdx.x, h = blockIdx.y;
+  const int b = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
   const int kvb = b / p.kv_group;
   const int lo = p.skip_len > 0 ? p.skip_lo + (b % p.kv_group) * p.skip_step : 0;
   const int hi = p.skip_len > 0 ? lo + p.skip_len : 0;
+  // number of query tiles of this CTA that hold at least one real query
+  const int q0 = qblk * QT * AT_BM;
+  const int nqt = (QT == 2 && q0 + AT_BM < p.Nq) ? 2 : 1;
 
-  if (warp == 0 && elect_one()) {
+  // this CTA's share [i0, i1) of the enumerated key tiles
+  int n_all = 0;
+  { TileWalk w(p.Nk0, p.Nk1, lo, hi); TileIt it; while (w.next(it)) ++n_all; }
+  const int chunk = (n_all + p.splits - 1) / p.splits;
+  const int i0 = split * chunk;
+  const int i1 = min(n_all, i0 + chunk);
+  const int n_tiles = max(i1 - i0, 0);
+
+  if (warp == TMA_WARP && elect_one()) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK0); tma_prefetch_desc(&tmV0);
     if (p.Nk1 > 0) { tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
     mbar_init(q_full, 1);
     for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_full[s], 1); mbar_init(&s_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, AT_TMEM_COLS); tmem_relinquish(); }
+  if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, h * HD, qt * AT_BM, b);
+    if (elect_one() && n_tiles > 0) {
+      mbar_arrive_expect_tx(q_full, nqt * TILE_BYTES);
+      for (int x = 0; x < nqt; ++x) tma_load_3d(sQ + x * TILE_BYTES, &tmQ, q_full, h * HD, q0 + x * AT_BM, b);
       TileWalk walk(p.Nk0, p.Nk1, lo, hi);
       TileIt it;
-      int i = 0;
+      int i = 0, j = 0;
       while (walk.next(it)) {
-        const int st = i % KS;
-        const uint32_t ph = (i / KS) & 1;
-        const CUtensorMap* mk = it.seg == 0 ? &tmK0 : &tmK1;
-        const CUtensorMap* mv = it.seg == 0 ? &tmV0 : &tmV1;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-        tma_load_3d(sK + st * TILE_BYTES, mk, &k_full[st], h * HD, it.t * AT_BN, kvb);
-        mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-        tma_load_3d(sV + st * TILE_BYTES, mv, &v_full[st], h * HD, it.t * AT_BN, kvb);
+        if (i >= i0 && i < i1) {
+          const int st = j % KS;
+          const uint32_t ph = (j / KS) & 1;
+          const CUtensorMap* mk = it.seg == 0 ? &tmK0 : &tmK1;
+          const CUtensorMap* mv = it.seg == 0 ? &tmV0 : &tmV1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+          tma_load_3d(sK + st * TILE_BYTES, mk, &k_full[st], h * HD, it.t * AT_BN, kvb);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+          tma_load_3d(sV + st * TILE_BYTES, mv, &v_full[st], h * HD, it.t * AT_BN, kvb);
+          ++j;
+        }
         ++i;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t bf = p.is_bf16 ? 1u : 0u;
-    const uint32_t idesc_qk = make_idesc(AT_BM, AT_BN, bf, 0, 0);   // S[128 x 128] = Q (K-major) * K^T (K-major)
-    const uint32_t idesc_pv = make_idesc(AT_BM, HD, bf, 0, 1);      // O[128 x 64]  = P (TMEM)   * V (MN-major)
-    int n_tiles = 0;
-    { TileWalk w(p.Nk0, p.Nk1, lo, hi); TileIt it; while (w.next(it)) ++n_tiles; }
-    const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ));
-    auto issue_qk = [&](int i) {
-      const int st = i % KS;
-      const int buf = i & 1;
-      mbar_wait(&k_full[st], (i / KS) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t kdesc = smem_desc_sw128(smem_u32(sK + st * TILE_BYTES));
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_base + buf * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[buf]);
-      }
-      __syncwarp();
-    };
+    constexpr uint32_t bf = BF16 ? 1u : 0u;
+    constexpr uint32_t idesc_qk = make_idesc(AT_BM, AT_BN, bf, 0, 0);   // S[128 x 128] = Q (K-major) * K^T (K-major)
+    constexpr uint32_t idesc_pv = make_idesc(AT_BM, HD, bf, 0, 1);      // O[128 x 64] += P (TMEM)   * V (MN-major)
     if (n_tiles > 0) {
       mbar_wait(q_full, 0);
       tc_fence_after();
-      issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
-      for (int i = 0; i < n_tiles; ++i) {
-        const int st = i % KS;
-        const int buf = i & 1;
-        mbar_wait(&p_full[buf], (i >> 1) & 1);
-        mbar_wait(&v_full[st], (i / KS) & 1);
-        tc_fence_after();
+      auto issue_qk = [&](int x, int j, bool release_k) {       // S_x = Q_x K(j)^T
+        const int st = j % KS;
+        if (elect_one()) {
+          const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ + x * TILE_BYTES));
+          const uint64_t kdesc = smem_desc_sw128(smem_u32(sK + st * TILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_base + x * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
+          umma_commit(&s_full[x]);
+          if (release_k) umma_commit(&k_empty[st]);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int x, int j, bool release_v) {       // O_x (+)= P_x V(j)
+        const int st = j % KS;
         if (elect_one()) {
           const uint64_t vdesc = smem_desc_sw128(smem_u32(sV + st * TILE_BYTES));
 #pragma unroll
           for (int k = 0; k < AT_BN / 16; ++k) {
             // 16 keys per MMA: P advances 8 TMEM columns (packed pairs), V advances 16 rows = 2048 B
-            umma_ts(tmem_base + buf * 128 + 64, tmem_base + buf * 128 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, k ? 1u : 0u);
+            umma_ts(tmem_base + QT * 128 + x * 64, tmem_base + x * 128 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv,
+                    (j | k) ? 1u : 0u);
           }
-          umma_commit(&v_empty[st]);
-          umma_commit(&o_full[buf]);
+          umma_commit(&o_done[x]);
+          if (release_v) umma_commit(&v_empty[st]);
         }
         __syncwarp();
-        if (i + 2 < n_tiles) {
-          mbar_wait(&s_empty[buf], (i >> 1) & 1);   // softmax has read O_i: buffer may be overwritten
+      };
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int x = 0; x < nqt; ++x) issue_qk(x, 0, x == nqt - 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        const bool more = j + 1 < n_tiles;
+        for (int x = 0; x < nqt; ++x) {
+          mbar_wait(&p_full[x], j & 1);
+          if (x == 0) mbar_wait(&v_full[j % KS], (j / KS) & 1);
           tc_fence_after();
-          issue_qk(i + 2);
+          issue_pv(x, j, x == nqt - 1);
+          if (more) {
+            if (x == 0) { mbar_wait(&k_full[(j + 1) % KS], ((j + 1) / KS) & 1); tc_fence_after(); }
+            issue_qk(x, j + 1, x == nqt - 1);      // in-order tensor pipe: PV_x(j) has read P_x before S_x is rewritten
+          }
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ softmax warps
+  } else if (warp < 4 * nqt) {
+    // ------------------------------------------------------------------ softmax warpgroup x
+    const int x = warp >> 2;
     const int quarter = warp & 3;
     const int lane = threadIdx.x & 31;
     const int row = quarter * 32 + lane;
-    const int q_idx = qt * AT_BM + row;
+    const int q_idx = q0 + x * AT_BM + row;
     const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
-    float m_run = -INFINITY, l_run = 0.f, alpha_pending = 1.f;
-    float acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-
-    auto drain_o = [&](int i, float alpha) {
-      const int buf = i & 1;
-      mbar_wait(&o_full[buf], (i >> 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(lane_addr + buf * 128 + 64 + c * 32, raw);
-        tmem_wait_ld();
-#pragma unroll
-        for (int d = 0; d < 32; ++d) acc[c * 32 + d] = fmaf(acc[c * 32 + d], alpha, __uint_as_float(raw[d]));
-      }
-      tc_fence_before();
-      mbar_arrive(&s_empty[buf]);
-    };
+    const uint32_t s_addr = lane_addr + x * 128;
+    const uint32_t o_addr = lane_addr + QT * 128 + x * 64;
+    float m_used = -INFINITY;      // max currently folded into the exponent (raw score units)
+    float l_run = 0.f;
 
     TileWalk walk(p.Nk0, p.Nk1, lo, hi);
     TileIt it;
-    int i = 0;
+    int i = 0, j = 0;
     while (walk.next(it)) {
-      const int buf = i & 1;
-      mbar_wait(&s_full[buf], (i >> 1) & 1);
+      if (i < i0 || i >= i1) { ++i; continue; }
+      ++i;
+      mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
-      const uint32_t s_addr = lane_addr + buf * 128;
-      // ---- pass 1: row max
-      float mx = m_run;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(s_addr + c * 32, raw);
-        tmem_wait_ld();
-        if (it.mask) {
+      uint32_t raw[128];
+      tmem_ld32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+      tmem_ld32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+      tmem_ld32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[64]));
+      tmem_ld32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&raw[96]));
+      tmem_wait_ld();
+      if (it.mask) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c * 32 + j, g = it.g0 + col;
-            const bool ok = col < it.nvalid && !(g >= lo && g < hi);
-            mx = fmaxf(mx, ok ? __uint_as_float(raw[j]) : -INFINITY);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(raw[j]));
+        for (int c = 0; c < 128; ++c) {
+          const int g = it.g0 + c;
+          const bool ok = c < it.nvalid && !(g >= lo && g < hi);
+          if (!ok) raw[c] = 0xff800000u;            // -inf
         }
       }
-      const float m_safe = (mx == -INFINITY) ? 0.f : mx;
-      const float alpha = exp2f((m_run - m_safe) * p.sl2);    // m_run = -inf -> 0
-      const float moff = m_safe * p.sl2;
-      // ---- pass 2: P = exp2(S*sl2 - m*sl2), row sum, pack to 16-bit, store over S_b[0,64)
-      float rsum = 0.f;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(raw[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(raw[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(raw[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(raw[c + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // lazy rescaling: refresh the folded max only when it is stale by more than 2^8
+      float alpha = 1.f;
+      bool refresh = false;
+      if (mx > -INFINITY && (m_used == -INFINITY || (mx - m_used) * p.sl2 > RESCALE_THRESHOLD)) {
+        refresh = true;
+        alpha = (m_used == -INFINITY) ? 0.f : ex2((m_used - mx) * p.sl2);
+        m_used = mx;
+      }
+      if (j > 0 && __any_sync(0xffffffffu, refresh)) {
+        // O_x *= alpha (per row).  P_x(j-1) V(j-1) must have landed first.
+        mbar_wait(&o_done[x], (j - 1) & 1);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        tmem_ld32(s_addr + c * 32, raw);
-        tmem_wait_ld();
-        float pv[32];
-        if (it.mask) {
+        for (int c = 0; c < 8; ++c) {               // rare path: small chunks keep the register footprint low
+          uint32_t o[8];
+          tmem_ld8(o_addr + c * 8, o);
+          tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = c * 32 + j, g = it.g0 + col;
-            const bool ok = col < it.nvalid && !(g >= lo && g < hi);
-            pv[j] = ok ? exp2f(fmaf(__uint_as_float(raw[j]), p.sl2, -moff)) : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) pv[j] = exp2f(fmaf(__uint_as_float(raw[j]), p.sl2, -moff));
+          for (int d = 0; d < 8; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+          tmem_st8(o_addr + c * 8, o);
         }
+        tmem_wait_st();
+      }
+      l_run *= alpha;
+      const float moff = (m_used == -INFINITY) ? 0.f : m_used * p.sl2;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          rsum += pv[2 * j] + pv[2 * j + 1];
-          pk[j] = pack16(pv[2 * j], pv[2 * j + 1], p.is_bf16);
+        for (int t = 0; t < 16; t += 2) {
+          const float a0 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t]), p.sl2, -moff));
+          const float a1 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 1]), p.sl2, -moff));
+          const float a2 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 2]), p.sl2, -moff));
+          const float a3 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 3]), p.sl2, -moff));
+          r0 += a0; r1 += a1; r2 += a2; r3 += a3;
+          pk[t] = packp<BF16>(a0, a1);
+          pk[t + 1] = packp<BF16>(a2, a3);
         }
         tmem_st16(s_addr + c * 16, pk);
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[buf]);
-      l_run = l_run * alpha + rsum;
-      m_run = mx;
-      // ---- fold the previous tile's P V product into the register accumulator
-      if (i > 0) drain_o(i - 1, alpha_pending);
-      alpha_pending = alpha;
-      ++i;
+      mbar_arrive(&p_full[x]);
+      l_run += (r0 + r1) + (r2 + r3);
+      ++j;
     }
-    if (i > 0) drain_o(i - 1, alpha_pending);
 
-    if (q_idx < p.Nq) {
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      uint16_t* orow = reinterpret_cast<uint16_t*>(p.O) + ((long long)b * p.Nq + q_idx) * p.ldo + h * HD;
-      uint4* o4 = reinterpret_cast<uint4*>(orow);
+    // ---- epilogue: wait for the last P V, normalise, store
+    uint32_t accr[HD];
+    if (j > 0) {
+      mbar_wait(&o_done[x], (j - 1) & 1);
+      tc_fence_after();
+      tmem_ld32(o_addr, *reinterpret_cast<uint32_t(*)[32]>(&accr[0]));
+      tmem_ld32(o_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&accr[32]));
+      tmem_wait_ld();
+    } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint4 w;
-        w.x = pack16(acc[8 * j] * inv, acc[8 * j + 1] * inv, p.is_bf16);
-        w.y = pack16(acc[8 * j + 2] * inv, acc[8 * j + 3] * inv, p.is_bf16);
-        w.z = pack16(acc[8 * j + 4] * inv, acc[8 * j + 5] * inv, p.is_bf16);
-        w.w = pack16(acc[8 * j + 6] * inv, acc[8 * j + 7] * inv, p.is_bf16);
-        o4[j] = w;
+      for (int d = 0; d < HD; ++d) accr[d] = 0u;
+    }
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = __uint_as_float(accr[d]);
+    if (q_idx < p.Nq) {
+      const long long grow = (long long)b * p.Nq + q_idx;
+      if (p.splits == 1) {
+        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          uint4 w;
+          w.x = packp<BF16>(acc[8 * t] * inv, acc[8 * t + 1] * inv);
+          w.y = packp<BF16>(acc[8 * t + 2] * inv, acc[8 * t + 3] * inv);
+          w.z = packp<BF16>(acc[8 * t + 4] * inv, acc[8 * t + 5] * inv);
+          w.w = packp<BF16>(acc[8 * t + 6] * inv, acc[8 * t + 7] * inv);
+          o4[t] = w;
+        }
+      } else {
+        float4* o4 = reinterpret_cast<float4*>(p.part_o + ((long long)split * p.rows_total + grow) * (p.H * HD) + h * HD);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) o4[t] = make_float4(acc[4 * t], acc[4 * t + 1], acc[4 * t + 2], acc[4 * t + 3]);
+        float2* ml = reinterpret_cast<float2*>(p.part_ml) + ((long long)split * p.rows_total + grow) * p.H + h;
+        *ml = make_float2(m_used == -INFINITY ? -INFINITY : m_used * p.sl2, l_run);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
+// Merge the key-range splits: out = sum_s O_s 2^(m_s - m) / sum_s l_s 2^(m_s - m).  One thread per (row, head, 8 dims).
+template <bool BF16>
+__global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                                                           int splits, long long rows, int H, uint16_t* __restrict__ out,
+                                                           long long ldo) {
+  const long long total = rows * H * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d8 = int(i & 7);
+    const long long rh = i >> 3;
+    const int h = int(rh % H);
+    const long long row = rh / H;
+    float m = -INFINITY;
+    for (int s = 0; s < splits; ++s) m = fmaxf(m, part_ml[(((long long)s * rows + row) * H + h) * 2]);
+    float l = 0.f;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < splits; ++s) {
+      const float2 ml = *reinterpret_cast<const float2*>(part_ml + (((long long)s * rows + row) * H + h) * 2);
+      const float w = (ml.x == -INFINITY) ? 0.f : ex2(ml.x - m);
+      l += ml.y * w;
+      const float4* o = reinterpret_cast<const float4*>(part_o + ((long long)s * rows + row) * (H * HD) + h * HD + d8 * 8);
+      const float4 a = o[0], c = o[1];
+      acc[0] += a.x * w; acc[1] += a.y * w; acc[2] += a.z * w; acc[3] += a.w * w;
+      acc[4] += c.x * w; acc[5] += c.y * w; acc[6] += c.z * w; acc[7] += c.w * w;
+    }
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    uint4 wv;
+    wv.x = packp<BF16>(acc[0] * inv, acc[1] * inv);
+    wv.y = packp<BF16>(acc[2] * inv, acc[3] * inv);
+    wv.z = packp<BF16>(acc[4] * inv, acc[5] * inv);
+    wv.w = packp<BF16>(acc[6] * inv, acc[7] * inv);
+    *reinterpret_cast<uint4*>(out + row * ldo + h * HD + d8 * 8) = wv;
+  }
+}
+
+template <bool BF16, int QT>
+static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
+                       const CUtensorMap& tmV1, const AttnParams& p, int B, cudaStream_t s) {
+  using Cfg = AttnCfg<QT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<BF16, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((p.Nq + QT * AT_BM - 1) / (QT * AT_BM), p.H, B * p.splits);
+  attn_kernel<BF16, QT><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
+// scratch for the split path, grown on demand (stream-ordered)
+static float* g_split_buf = nullptr;
+static size_t g_split_cap = 0;
+
 }  // namespace m3r
 
+// Number of fp32 scratch elements m3r_attention may need for a problem (0 if it will not split).
 extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   using namespace m3r;
   if (!a || !a->Q || !a->K0 || !a->V0 || !a->O) return set_error("attention: null pointer");
@@ -318,6 +440,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     const int tot = a->Nk0 + a->Nk1;
     if (a->skip_len >= tot && a->skip_len > 0) return set_error("attention: skip range covers every key");
   }
+  cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
   const int Bkv = a->B / a->kv_group;
   CUtensorMap tmQ, tmK0, tmV0, tmK1, tmV1;
   auto mk3 = [&](CUtensorMap* m, const void* base, int64_t ld, int64_t rows, int64_t bstride_rows, int64_t nb) {
@@ -333,27 +456,58 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     if (mk3(&tmK1, a->K1, a->ldk1, a->Nk1, a->kv_bstride1, Bkv)) return 1;
     if (mk3(&tmV1, a->V1, a->ldk1, a->Nk1, a->kv_bstride1, Bkv)) return 1;
   } else { tmK1 = tmK0; tmV1 = tmV0; }
+
+  // ---- shape heuristics: 2 query tiles per CTA when that still fills the GPU; otherwise 1 tile + key splits
+  const int sms = num_sms();
+  const int key_tiles = (a->Nk0 + AT_BN - 1) / AT_BN + (a->Nk1 + AT_BN - 1) / AT_BN;   // upper bound
+  int qt = 2;
+  const int ctas2 = ((a->Nq + 255) / 256) * a->H * a->B;
+  const int ctas1 = ((a->Nq + 127) / 128) * a->H * a->B;
+  if (a->Nq <= 128 || ctas2 < sms) qt = 1;
+  int splits = 1;
+  if (qt == 1 && ctas1 < sms) {
+    splits = (2 * sms + ctas1 - 1) / ctas1;            // aim at ~2 CTAs per SM worth of work items
+    if (splits > key_tiles) splits = key_tiles;
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
+  }
+  if (const char* f = getenv("M3R_ATTN_QT")) { const int v = atoi(f); if (v == 1 || v == 2) qt = v; if (qt == 2) splits = 1; }
+  if (const char* f = getenv("M3R_ATTN_SPLITS")) { const int v = atoi(f); if (v >= 1 && v <= 16 && qt == 1) splits = v < key_tiles ? v : key_tiles; }
+
   AttnParams p;
   p.Nq = a->Nq; p.Nk0 = a->Nk0; p.Nk1 = a->Nk1; p.kv_group = a->kv_group;
   p.skip_lo = a->skip_lo; p.skip_step = a->skip_step; p.skip_len = a->skip_len;
-  p.is_bf16 = a->is_bf16; p.sl2 = a->scale * 1.4426950408889634f;
-  p.O = a->O; p.ldo = a->ldo;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    if (e != cudaSuccess) return set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  p.splits = splits; p.sl2 = a->scale * 1.4426950408889634f;
+  p.O = a->O; p.ldo = a->ldo; p.H = a->H; p.rows_total = (long long)a->B * a->Nq;
+  p.part_o = nullptr; p.part_ml = nullptr;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * p.rows_total * a->H * (HD + 2);
+    if (need > g_split_cap) {
+      if (g_split_buf) cudaFreeAsync(g_split_buf, cs);
+      g_split_buf = nullptr; g_split_cap = 0;
+      if (cudaMallocAsync(&g_split_buf, need * sizeof(float), cs) != cudaSuccess) return set_error("attention: split scratch allocation failed");
+      g_split_cap = need;
+    }
+    p.part_o = g_split_buf;
+    p.part_ml = g_split_buf + (size_t)splits * p.rows_total * a->H * HD;
   }
-  dim3 grid((a->Nq + AT_BM - 1) / AT_BM, a->H, a->B);
   {
     const double nk_eff = (double)(a->Nk0 + a->Nk1 - a->skip_len);
     ProfScope prof(PROF_ATTN, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
-                   2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)(a->B / a->kv_group) * (a->Nk0 + a->Nk1) * a->H * HD * 2),
-                   reinterpret_cast<cudaStream_t>(stream));
-    attn_kernel<<<grid, AT_THREADS, AT_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
+                   2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)Bkv * (a->Nk0 + a->Nk1) * a->H * HD * 2), cs);
+    int rc;
+    if (a->is_bf16) rc = qt == 2 ? launch_attn<true, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) : launch_attn<true, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs);
+    else rc = qt == 2 ? launch_attn<false, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) : launch_attn<false, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs);
+    if (rc) return rc;
+    if (splits > 1) {
+      const long long total = p.rows_total * a->H * 8;
+      const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
+      if (a->is_bf16) attn_combine_kernel<true><<<grid, 256, 0, cs>>>(p.part_o, p.part_ml, splits, p.rows_total, a->H, reinterpret_cast<uint16_t*>(a->O), a->ldo);
+      else attn_combine_kernel<false><<<grid, 256, 0, cs>>>(p.part_o, p.part_ml, splits, p.rows_total, a->H, reinterpret_cast<uint16_t*>(a->O), a->ldo);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return set_error("attention combine launch: %s", cudaGetErrorString(e));
+      count_launch();
+    }
   }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
-  count_launch();
   return 0;
 }

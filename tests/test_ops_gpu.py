@@ -178,6 +178,41 @@ def test_memory_cross_attention(dtype, Nm, n, N):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("qt,splits", [(1, 1), (1, 3), (1, 16), (2, 1)])
+def test_attention_kernel_variants(dtype, qt, splits, monkeypatch):
+    """Force each kernel configuration (1 or 2 query tiles per CTA, key-range splits + combine) on a masked,
+    two-segment, ragged problem and on a long-key problem with large score spread (exercises the lazy rescale)."""
+    monkeypatch.setenv("M3R_ATTN_QT", str(qt))
+    monkeypatch.setenv("M3R_ATTN_SPLITS", str(splits))
+    B, H, n, N, Nm = 1, 3, 2, 300, 700
+    D = H * 64
+    mem = rnd(B, Nm, 2 * D, dtype=dtype, seed=30)
+    new = rnd(B, n * N, 2 * D, dtype=dtype, seed=31)
+    q = rnd(B * n * N, D, dtype=dtype, seed=32, scale=3.0)          # wide score range -> max refreshes
+    out = ops.attention(q, mem.view(-1, 2 * D)[:, :D], mem.view(-1, 2 * D)[:, D:], B=B * n, H=H, Nq=N, Nk0=Nm,
+                        k1=new.view(-1, 2 * D)[:, :D], v1=new.view(-1, 2 * D)[:, D:], Nk1=n * N, kv_group=n,
+                        skip_lo=Nm, skip_step=N, skip_len=N)
+    kv = torch.cat([mem, new], 1)
+    Nk = kv.shape[1]
+    k = kv[..., :D].view(B, 1, Nk, H, 64).expand(B, n, Nk, H, 64).reshape(B * n, Nk, H, 64).permute(0, 2, 1, 3)
+    v = kv[..., D:].view(B, 1, Nk, H, 64).expand(B, n, Nk, H, 64).reshape(B * n, Nk, H, 64).permute(0, 2, 1, 3)
+    mask = torch.ones(B * n, 1, 1, Nk, dtype=torch.bool, device="cuda")
+    for j in range(B * n):
+        mask[j, ..., Nm + (j % n) * N: Nm + (j % n + 1) * N] = False
+    ref = ref_attn(q.view(B * n, N, H, 64).permute(0, 2, 1, 3), k, v, mask).permute(0, 2, 1, 3).reshape(B * n * N, D)
+    assert torch.isfinite(out.float()).all()
+    assert rel_l2(out, ref) < ATT_TOL[dtype]
+    # keys sorted so that the row max keeps growing tile after tile
+    Nk2 = 2048
+    kk = rnd(Nk2, 64, dtype=torch.float32, seed=33)
+    kk = (kk * torch.linspace(0.2, 4.0, Nk2, device="cuda")[:, None]).to(dtype)
+    vv = rnd(Nk2, 64, dtype=dtype, seed=34)
+    qq = rnd(256, 64, dtype=dtype, seed=35, scale=2.0)
+    out = ops.attention(qq, kk, vv, B=1, H=1, Nq=256, Nk0=Nk2)
+    assert rel_l2(out, ref_attn(qq, kk, vv)) < ATT_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DT)
 def test_render_cross_attention_long_memory(dtype):
     """Render mode: 4 views against a 20-view memory (Nmem = 15360), no mask, shared K/V (decoder.py:307-317)."""
     H, N, Nm, n = 12, 768, 15360, 4

@@ -1,0 +1,56 @@
+"""Stand-alone timing of the attention / GEMM kernels at the shapes of the C3 job (CUDA events, L2 flushed between
+iterations by a 256 MB write).  `python tools/prof_attn.py [attn|gemm] [--once]`; --once runs each shape twice for ncu."""
+import os, sys, time
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from must3r_b200 import ops  # noqa: E402
+
+once = "--once" in sys.argv
+which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["attn", "gemm"]
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+
+def timeit(fn, iters=10):
+    fn(); fn()
+    if once:
+        torch.cuda.synchronize(); return 0.0
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+dt = torch.bfloat16
+if "attn" in which:
+    for name, (B, H, Nq, Nk, grp) in {
+        "render CA 20 views x M=20": (20, 12, 768, 15360, 20),
+        "render CA 4 views x M=20": (4, 12, 768, 15360, 4),
+        "update CA 1 view x M=10": (1, 12, 768, 7680, 1),
+        "update CA 1 view x M=19": (1, 12, 768, 14592, 1),
+        "decoder SA 1 view": (1, 12, 768, 768, 1),
+        "encoder SA 20 views": (20, 16, 768, 768, 1),
+    }.items():
+        D = H * 64
+        q = torch.randn(B * Nq, D, device="cuda").to(dt)
+        nb = B // grp if grp > 1 else B
+        kv = torch.randn(nb * Nk, 2 * D, device="cuda").to(dt)
+        fn = lambda: ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk, kv_group=grp if grp > 1 else 1)  # noqa: E731
+        ms = timeit(fn)
+        fl = 4.0 * B * H * Nq * Nk * 64
+        print(f"attn {name:28s} {ms*1e3:9.1f} us  {fl/ms/1e9 if ms else 0:8.1f} TFLOP/s", flush=True)
+if "gemm" in which:
+    for name, (M, N, K) in {
+        "enc qkv 20v": (15360, 3072, 1024), "enc proj 20v": (15360, 1024, 1024), "enc fc1 20v": (15360, 4096, 1024),
+        "enc fc2 20v": (15360, 1024, 4096), "dec qkv 20v": (15360, 2304, 768), "dec fc1 20v": (15360, 3072, 768),
+        "dec fc2 20v": (15360, 768, 3072), "dec head 20v": (15360, 1792, 768),
+        "dec qkv 1v": (768, 2304, 768), "dec proj 1v": (768, 768, 768), "dec kv 1v": (768, 1536, 768),
+        "dec fc1 1v": (768, 3072, 768), "dec fc2 1v": (768, 768, 3072),
+    }.items():
+        a = torch.randn(M, K, device="cuda").to(dt); w = torch.randn(N, K, device="cuda").to(dt)
+        out = torch.empty(M, N, device="cuda", dtype=dt)
+        ms = timeit(lambda: ops.linear(a, w, None, out=out))
+        print(f"gemm {name:14s} M={M:6d} N={N:5d} K={K:5d} {ms*1e3:9.1f} us  {2.0*M*N*K/ms/1e9 if ms else 0:8.1f} TFLOP/s", flush=True)
