@@ -4,8 +4,10 @@
 // share every K / V tile that TMA brings in (half the L2->smem traffic) and ping-pong on the tensor pipe, so one
 // tile's softmax overlaps the other's MMAs.  Roles:
 //   warps 0..4*QT-1 : softmax warpgroup per query tile -- ONE query row per thread (TMEM lane == row, so row max /
-//                     row sum need no shuffles); single pass over S held in registers: row max, exp2 with the
-//                     scale folded in, row sum, pack P to 16-bit and store it over S's own TMEM columns.
+//                     row sum need no shuffles); keys are consumed in half tiles of 64: single pass over the 64
+//                     scores held in registers: row max, exp2 with the scale folded in, row sum, pack P to 16-bit
+//                     and store it over S's own TMEM columns.  S is double-buffered per warpgroup so Q K^T of half
+//                     tile j+1 is already in TMEM when the softmax of half tile j ends.
 //   warp 4*QT       : TMA producer -- Q tiles once, then K and V tiles (128 keys x 64) through mbarrier rings.
 //                     3-D tensor maps: rows beyond Nk read as zeros even inside over-allocated memory buffers.
 //   warp 4*QT+1     : TMEM allocator + single-thread MMA issuer:  S = Q K^T (both operands K-major smem),
@@ -14,7 +16,8 @@
 // O accumulates in TMEM across key tiles.  The running max used in the exponent is only refreshed when the true
 // row max grew by more than 2^8 (lazy rescaling): the rare refresh multiplies O in TMEM by the correction factor;
 // the final O / l is mathematically unchanged.
-// TMEM columns (QT=2): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384); P_x aliases S_x[0,64).
+// TMEM columns (QT=2): S_A0 [0,64) S_A1 [64,128) S_B0 [128,192) S_B1 [192,256) O_A [256,320) O_B [320,384);
+// P_x(j) (packed 16-bit pairs, 32 columns) aliases the first half of the S buffer it was computed from.
 //
 // Keys come from two segments (stored memory + this step's new tokens) so the reference's torch.cat of the memory
 // (decoder.py:306) never happens; a per-batch skip range implements make_mem_mask (decoder.py:119-139): fully
@@ -115,9 +118,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* k_empty = k_full + KS;     // [KS]
   uint64_t* v_full = k_empty + KS;     // [KS]
   uint64_t* v_empty = v_full + KS;     // [KS]
-  uint64_t* s_full = v_empty + KS;     // [2]   MMA -> softmax x : S_x(j) ready
-  uint64_t* p_full = s_full + 2;       // [2]   softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
-  uint64_t* o_done = p_full + 2;       // [2]   MMA -> softmax x : P_x(j) V(j) accumulated into O_x
+  uint64_t* s_full = v_empty + KS;     // [2][2] MMA -> softmax x : S_x(j) ready in buffer j&1
+  uint64_t* p_full = s_full + 4;       // [2][2] softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
+  uint64_t* o_done = p_full + 4;       // [2]    MMA -> softmax x : P_x(j) V(j) accumulated into O_x
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -143,7 +146,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (p.Nk1 > 0) { tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
     mbar_init(q_full, 1);
     for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
+    for (int s = 0; s < 2; ++s) mbar_init(&o_done[s], 1);
     fence_mbar_init();
   }
   if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -151,6 +155,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();
+  griddep_launch();
 
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------ TMA producer
@@ -180,52 +186,53 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t bf = BF16 ? 1u : 0u;
-    constexpr uint32_t idesc_qk = make_idesc(AT_BM, AT_BN, bf, 0, 0);   // S[128 x 128] = Q (K-major) * K^T (K-major)
-    constexpr uint32_t idesc_pv = make_idesc(AT_BM, HD, bf, 0, 1);      // O[128 x 64] += P (TMEM)   * V (MN-major)
+    constexpr uint32_t idesc_qk = make_idesc(AT_BM, 64, bf, 0, 0);      // S[128 x 64] = Q (K-major) * K_half^T (K-major)
+    constexpr uint32_t idesc_pv = make_idesc(AT_BM, HD, bf, 0, 1);      // O[128 x 64] += P (TMEM)   * V_half (MN-major)
     if (n_tiles > 0) {
+      const int n_half = 2 * n_tiles;                            // half tiles of 64 keys
       mbar_wait(q_full, 0);
       tc_fence_after();
-      auto issue_qk = [&](int x, int j, bool release_k) {       // S_x = Q_x K(j)^T
-        const int st = j % KS;
+      auto issue_qk = [&](int x, int j) {                        // S_x[j&1] = Q_x K(j)^T ; K(j) = rows (j&1)*64.. of tile j/2
+        const int t = j >> 1, st = t % KS;
         if (elect_one()) {
           const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ + x * TILE_BYTES));
-          const uint64_t kdesc = smem_desc_sw128(smem_u32(sK + st * TILE_BYTES));
+          const uint64_t kdesc = smem_desc_sw128(smem_u32(sK + st * TILE_BYTES + (j & 1) * 64 * 128));
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_base + x * 128, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
-          umma_commit(&s_full[x]);
-          if (release_k) umma_commit(&k_empty[st]);
+          for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_base + x * 128 + (j & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
+          umma_commit(&s_full[x * 2 + (j & 1)]);
+          if ((j & 1) && x == nqt - 1) umma_commit(&k_empty[st]);      // last reader of this K tile
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int x, int j, bool release_v) {       // O_x (+)= P_x V(j)
-        const int st = j % KS;
+      auto issue_pv = [&](int x, int j) {                        // O_x (+)= P_x(j) V(j)
+        const int t = j >> 1, st = t % KS;
         if (elect_one()) {
-          const uint64_t vdesc = smem_desc_sw128(smem_u32(sV + st * TILE_BYTES));
+          const uint64_t vdesc = smem_desc_sw128(smem_u32(sV + st * TILE_BYTES + (j & 1) * 64 * 128));
 #pragma unroll
-          for (int k = 0; k < AT_BN / 16; ++k) {
+          for (int k = 0; k < 64 / 16; ++k) {
             // 16 keys per MMA: P advances 8 TMEM columns (packed pairs), V advances 16 rows = 2048 B
-            umma_ts(tmem_base + QT * 128 + x * 64, tmem_base + x * 128 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv,
+            umma_ts(tmem_base + QT * 128 + x * 64, tmem_base + x * 128 + (j & 1) * 64 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv,
                     (j | k) ? 1u : 0u);
           }
           umma_commit(&o_done[x]);
-          if (release_v) umma_commit(&v_empty[st]);
+          if ((j & 1) && x == nqt - 1) umma_commit(&v_empty[st]);
         }
         __syncwarp();
       };
+      // prologue: the first two half tiles of every query tile
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      for (int x = 0; x < nqt; ++x) issue_qk(x, 0, x == nqt - 1);
-      for (int j = 0; j < n_tiles; ++j) {
-        const bool more = j + 1 < n_tiles;
+      for (int j = 0; j < 2; ++j)
+        for (int x = 0; x < nqt; ++x) issue_qk(x, j);
+      for (int j = 0; j < n_half; ++j) {
+        if ((j & 1) == 0) { mbar_wait(&v_full[(j >> 1) % KS], ((j >> 1) / KS) & 1); }
+        const bool more = j + 2 < n_half;
+        if (more && (j & 1) == 0) { const int t2 = (j + 2) >> 1; mbar_wait(&k_full[t2 % KS], (t2 / KS) & 1); }
         for (int x = 0; x < nqt; ++x) {
-          mbar_wait(&p_full[x], j & 1);
-          if (x == 0) mbar_wait(&v_full[j % KS], (j / KS) & 1);
+          mbar_wait(&p_full[x * 2 + (j & 1)], (j >> 1) & 1);
           tc_fence_after();
-          issue_pv(x, j, x == nqt - 1);
-          if (more) {
-            if (x == 0) { mbar_wait(&k_full[(j + 1) % KS], ((j + 1) / KS) & 1); tc_fence_after(); }
-            issue_qk(x, j + 1, x == nqt - 1);      // in-order tensor pipe: PV_x(j) has read P_x before S_x is rewritten
-          }
+          issue_pv(x, j);
+          if (more) issue_qk(x, j + 2);   // in-order tensor pipe: P V (j) has read P_x before buffer j&1 is rewritten
         }
       }
     }
@@ -244,81 +251,82 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
     TileWalk walk(p.Nk0, p.Nk1, lo, hi);
     TileIt it;
-    int i = 0, j = 0;
+    int i = 0, j = 0;                 // j counts half tiles of 64 keys
     while (walk.next(it)) {
       if (i < i0 || i >= i1) { ++i; continue; }
       ++i;
-      mbar_wait(&s_full[x], j & 1);
-      tc_fence_after();
-      uint32_t raw[128];
-      tmem_ld32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
-      tmem_ld32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
-      tmem_ld32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[64]));
-      tmem_ld32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&raw[96]));
-      tmem_wait_ld();
-      if (it.mask) {
-#pragma unroll
-        for (int c = 0; c < 128; ++c) {
-          const int g = it.g0 + c;
-          const bool ok = c < it.nvalid && !(g >= lo && g < hi);
-          if (!ok) raw[c] = 0xff800000u;            // -inf
-        }
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(raw[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(raw[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(raw[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(raw[c + 3]));
-      }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      // lazy rescaling: refresh the folded max only when it is stale by more than 2^8
-      float alpha = 1.f;
-      bool refresh = false;
-      if (mx > -INFINITY && (m_used == -INFINITY || (mx - m_used) * p.sl2 > RESCALE_THRESHOLD)) {
-        refresh = true;
-        alpha = (m_used == -INFINITY) ? 0.f : ex2((m_used - mx) * p.sl2);
-        m_used = mx;
-      }
-      if (j > 0 && __any_sync(0xffffffffu, refresh)) {
-        // O_x *= alpha (per row).  P_x(j-1) V(j-1) must have landed first.
-        mbar_wait(&o_done[x], (j - 1) & 1);
-        tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < 8; ++c) {               // rare path: small chunks keep the register footprint low
-          uint32_t o[8];
-          tmem_ld8(o_addr + c * 8, o);
-          tmem_wait_ld();
+      for (int hh = 0; hh < 2; ++hh, ++j) {
+        const int buf = j & 1;
+        mbar_wait(&s_full[x * 2 + buf], (j >> 1) & 1);
+        tc_fence_after();
+        uint32_t raw[64];
+        tmem_ld32(s_addr + buf * 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+        tmem_ld32(s_addr + buf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+        tmem_wait_ld();
+        if (it.mask) {
 #pragma unroll
-          for (int d = 0; d < 8; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
-          tmem_st8(o_addr + c * 8, o);
+          for (int c = 0; c < 64; ++c) {
+            const int col = hh * 64 + c, g = it.g0 + col;
+            const bool ok = col < it.nvalid && !(g >= lo && g < hi);
+            if (!ok) raw[c] = 0xff800000u;            // -inf
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(raw[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(raw[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(raw[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(raw[c + 3]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // lazy rescaling: refresh the folded max only when it is stale by more than 2^8
+        float alpha = 1.f;
+        bool refresh = false;
+        if (mx > -INFINITY && (m_used == -INFINITY || (mx - m_used) * p.sl2 > RESCALE_THRESHOLD)) {
+          refresh = true;
+          alpha = (m_used == -INFINITY) ? 0.f : ex2((m_used - mx) * p.sl2);
+          m_used = mx;
+        }
+        if (j > 0 && __any_sync(0xffffffffu, refresh)) {
+          // O_x *= alpha (per row).  P_x(j-1) V(j-1) must have landed first.
+          mbar_wait(&o_done[x], (j - 1) & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 8; ++c) {               // rare path: small chunks keep the register footprint low
+            uint32_t o[8];
+            tmem_ld8(o_addr + c * 8, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int d = 0; d < 8; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+            tmem_st8(o_addr + c * 8, o);
+          }
+          tmem_wait_st();
+        }
+        l_run *= alpha;
+        const float moff = (m_used == -INFINITY) ? 0.f : m_used * p.sl2;
+        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int t = 0; t < 16; t += 2) {
+            const float a0 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t]), p.sl2, -moff));
+            const float a1 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 1]), p.sl2, -moff));
+            const float a2 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 2]), p.sl2, -moff));
+            const float a3 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 3]), p.sl2, -moff));
+            r0 += a0; r1 += a1; r2 += a2; r3 += a3;
+            pk[t] = packp<BF16>(a0, a1);
+            pk[t + 1] = packp<BF16>(a2, a3);
+          }
+          tmem_st16(s_addr + buf * 64 + c * 16, pk);
         }
         tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[x * 2 + buf]);
+        l_run += (r0 + r1) + (r2 + r3);
       }
-      l_run *= alpha;
-      const float moff = (m_used == -INFINITY) ? 0.f : m_used * p.sl2;
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int t = 0; t < 16; t += 2) {
-          const float a0 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t]), p.sl2, -moff));
-          const float a1 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 1]), p.sl2, -moff));
-          const float a2 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 2]), p.sl2, -moff));
-          const float a3 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 3]), p.sl2, -moff));
-          r0 += a0; r1 += a1; r2 += a2; r3 += a3;
-          pk[t] = packp<BF16>(a0, a1);
-          pk[t + 1] = packp<BF16>(a2, a3);
-        }
-        tmem_st16(s_addr + c * 16, pk);
-      }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[x]);
-      l_run += (r0 + r1) + (r2 + r3);
-      ++j;
     }
 
     // ---- epilogue: wait for the last P V, normalise, store
@@ -374,6 +382,8 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restri
                                                            int splits, long long rows, int H, uint16_t* __restrict__ out,
                                                            long long ldo) {
   const long long total = rows * H * 8;
+  griddep_wait();
+  griddep_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int d8 = int(i & 7);
     const long long rh = i >> 3;
@@ -413,8 +423,8 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CU
     attr_set = true;
   }
   dim3 grid((p.Nq + QT * AT_BM - 1) / (QT * AT_BM), p.H, B * p.splits);
-  attn_kernel<BF16, QT><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(tmQ, tmK0, tmV0, tmK1, tmV1, p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(attn_kernel<BF16, QT>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
   count_launch();
   return 0;
@@ -457,22 +467,23 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     if (mk3(&tmV1, a->V1, a->ldk1, a->Nk1, a->kv_bstride1, Bkv)) return 1;
   } else { tmK1 = tmK0; tmV1 = tmV0; }
 
-  // ---- shape heuristics: 2 query tiles per CTA when that still fills the GPU; otherwise 1 tile + key splits
+  // ---- shape heuristics: 2 query tiles per CTA (shared K/V, ping-pong) whenever there is more than one tile of
+  // queries; when that leaves SMs idle (one view per step) the key range is split over several CTAs.
   const int sms = num_sms();
   const int key_tiles = (a->Nk0 + AT_BN - 1) / AT_BN + (a->Nk1 + AT_BN - 1) / AT_BN;   // upper bound
-  int qt = 2;
-  const int ctas2 = ((a->Nq + 255) / 256) * a->H * a->B;
-  const int ctas1 = ((a->Nq + 127) / 128) * a->H * a->B;
-  if (a->Nq <= 128 || ctas2 < sms) qt = 1;
+  int qt = a->Nq > 128 ? 2 : 1;
+  if (const char* f = getenv("M3R_ATTN_QT")) { const int v = atoi(f); if (v == 1 || v == 2) qt = v; }
+  const int ctas = ((a->Nq + qt * 128 - 1) / (qt * 128)) * a->H * a->B;
   int splits = 1;
-  if (qt == 1 && ctas1 < sms) {
-    splits = (2 * sms + ctas1 - 1) / ctas1;            // aim at ~2 CTAs per SM worth of work items
-    if (splits > key_tiles) splits = key_tiles;
-    if (splits > 16) splits = 16;
-    if (splits < 1) splits = 1;
+  if (ctas < sms) {
+    splits = (sms + ctas - 1) / ctas;
+    if (const char* f = getenv("M3R_ATTN_WAVES")) { const double wv = atof(f); if (wv > 0) splits = (int)((wv * sms + ctas - 1) / ctas); }
   }
-  if (const char* f = getenv("M3R_ATTN_QT")) { const int v = atoi(f); if (v == 1 || v == 2) qt = v; if (qt == 2) splits = 1; }
-  if (const char* f = getenv("M3R_ATTN_SPLITS")) { const int v = atoi(f); if (v >= 1 && v <= 16 && qt == 1) splits = v < key_tiles ? v : key_tiles; }
+  if (const char* f = getenv("M3R_ATTN_SPLITS")) { const int v = atoi(f); if (v >= 1) splits = v; }
+  if (splits > key_tiles) splits = key_tiles;
+  if (splits > 32) splits = 32;
+  if (splits < 1) splits = 1;
+  { const int chunk = (key_tiles + splits - 1) / splits; splits = (key_tiles + chunk - 1) / chunk; }   // no empty splits
 
   AttnParams p;
   p.Nq = a->Nq; p.Nk0 = a->Nk0; p.Nk1 = a->Nk1; p.kv_group = a->kv_group;
@@ -502,9 +513,10 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     if (splits > 1) {
       const long long total = p.rows_total * a->H * 8;
       const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
-      if (a->is_bf16) attn_combine_kernel<true><<<grid, 256, 0, cs>>>(p.part_o, p.part_ml, splits, p.rows_total, a->H, reinterpret_cast<uint16_t*>(a->O), a->ldo);
-      else attn_combine_kernel<false><<<grid, 256, 0, cs>>>(p.part_o, p.part_ml, splits, p.rows_total, a->H, reinterpret_cast<uint16_t*>(a->O), a->ldo);
-      cudaError_t e = cudaGetLastError();
+      cudaError_t e;
+      if (a->is_bf16) e = launch_pdl(attn_combine_kernel<true>, dim3(grid), dim3(256), 0, cs, (const float*)p.part_o, (const float*)p.part_ml, splits, p.rows_total, a->H, reinterpret_cast<uint16_t*>(a->O), (long long)a->ldo);
+      else e = launch_pdl(attn_combine_kernel<false>, dim3(grid), dim3(256), 0, cs, (const float*)p.part_o, (const float*)p.part_ml, splits, p.rows_total, a->H, reinterpret_cast<uint16_t*>(a->O), (long long)a->ldo);
+      if (e == cudaSuccess) e = cudaGetLastError();
       if (e != cudaSuccess) return set_error("attention combine launch: %s", cudaGetErrorString(e));
       count_launch();
     }

@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int M, int D, void* __restrict__ out, long long ldo,
                                                         int out_dtype, int is_bf16) {
+  griddep_wait();
+  griddep_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -79,6 +81,8 @@ __global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ x
                                                      uint16_t* __restrict__ out, long long ldo, int is_bf16) {
   const int nv = D >> 2;
   const long long total = (long long)M * nv;
+  griddep_wait();
+  griddep_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int row = int(i / nv), c = int(i % nv);
     const float4 t = reinterpret_cast<const float4*>(x + (long long)row * ldx)[c];
@@ -92,6 +96,8 @@ __global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ x
 // ---------------------------------------------------------------------------------------------- RoPE
 // tab[t][0..15]=cos(y*w_d) [16..31]=sin(y*w_d) [32..47]=cos(x*w_d) [48..63]=sin(x*w_d), w_d = f0 / base^(d/16)
 __global__ void rope_table_kernel(const long long* __restrict__ pos, int T, float base, float f0, float* __restrict__ tab) {
+  griddep_wait();
+  griddep_launch();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * 32) return;
   const int t = i >> 5, axis = (i >> 4) & 1, d = i & 15;
@@ -116,6 +122,8 @@ __global__ void rope2d_kernel(T* __restrict__ tok, int B, int N, int H, int D, l
                               const long long* __restrict__ pos, float base, float fwd) {
   const int Q = D >> 2;
   const long long total = (long long)B * N * H * 2 * Q;
+  griddep_wait();
+  griddep_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int d = int(i % Q);
     const int axis = int((i / Q) % 2);
@@ -138,6 +146,8 @@ __global__ void __launch_bounds__(256) im2col16_kernel(const float* __restrict__
                                                        uint16_t* __restrict__ out, int is_bf16) {
   const int gw = W >> 4, gh = H >> 4;
   const long long total = (long long)V * 3 * H * (W >> 2);
+  griddep_wait();
+  griddep_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int xq = int(i % (W >> 2));          // float4 index along the image row
     long long r = i / (W >> 2);
@@ -160,6 +170,8 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict
                                                          float* __restrict__ out) {
   const int gw = W >> 4, gh = H >> 4;
   const long long total = (long long)V * H * W;
+  griddep_wait();
+  griddep_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int X = int(i % W);
     const int Y = int((i / W) % H);
@@ -175,6 +187,8 @@ __global__ void __launch_bounds__(256) unpatchify_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) postprocess_kernel(const float* __restrict__ pm, long long P,
                                                           float* __restrict__ pts3d, float* __restrict__ local,
                                                           float* __restrict__ conf) {
+  griddep_wait();
+  griddep_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
     const float* s = pm + i * 7;
     float a[7];
@@ -220,9 +234,9 @@ extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int6
   const int grid = (M + wpb - 1) / wpb;
   ProfScope prof(PROF_LN, 0.0, (double)M * D * (4.0 + (add ? 4.0 : 0.0) + (out_dtype ? 2.0 : 4.0)), s);
   if (D <= 1024)
-    layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, ldx, add, ldadd, gamma, beta, eps, M, D, out, ldo, out_dtype, is_bf16);
+    launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(wpb * 32), 0, s, x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
   else
-    layernorm_kernel<16><<<grid, wpb * 32, 0, s>>>(x, ldx, add, ldadd, gamma, beta, eps, M, D, out, ldo, out_dtype, is_bf16);
+    launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(wpb * 32), 0, s, x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
   return check_launch("layernorm");
 }
 
@@ -231,16 +245,16 @@ extern "C" int m3r_cast16(const float* x, int64_t ldx, int32_t M, int32_t D, voi
   if (!x || !out) return set_error("cast16: null pointer");
   if (M <= 0) return 0;
   if (D % 4 || ldx % 4 || ldo % 4) return set_error("cast16: alignment");
-  cast16_kernel<<<grid_for((long long)M * (D / 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, ldx, M, D, reinterpret_cast<uint16_t*>(out), ldo, is_bf16);
+  launch_pdl(cast16_kernel, dim3(grid_for((long long)M * (D / 4), 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             x, (long long)ldx, (int)M, (int)D, reinterpret_cast<uint16_t*>(out), (long long)ldo, (int)is_bf16);
   return check_launch("cast16");
 }
 
 extern "C" int m3r_rope_table(const int64_t* pos, int32_t T, float base, float f0, float* tab, void* stream) {
   if (!pos || !tab) return set_error("rope_table: null pointer");
   if (T <= 0) return 0;
-  rope_table_kernel<<<(T * 32 + 255) / 256, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const long long*>(pos), T, base, f0, tab);
+  launch_pdl(rope_table_kernel, dim3((T * 32 + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             reinterpret_cast<const long long*>(pos), (int)T, base, f0, tab);
   return check_launch("rope_table");
 }
 
@@ -253,9 +267,9 @@ extern "C" int m3r_rope_2d(void* tokens, int32_t dtype, int32_t B, int32_t N, in
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int grid = grid_for(total, 256);
   const long long* p = reinterpret_cast<const long long*>(pos);
-  if (dtype == 0) rope2d_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<float*>(tokens), B, N, H, D, sB, sN, sH, p, base, fwd);
-  else if (dtype == 1) rope2d_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<__half*>(tokens), B, N, H, D, sB, sN, sH, p, base, fwd);
-  else if (dtype == 2) rope2d_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(tokens), B, N, H, D, sB, sN, sH, p, base, fwd);
+  if (dtype == 0) launch_pdl(rope2d_kernel<float>, dim3(grid), dim3(256), 0, s, reinterpret_cast<float*>(tokens), (int)B, (int)N, (int)H, (int)D, (long long)sB, (long long)sN, (long long)sH, p, base, fwd);
+  else if (dtype == 1) launch_pdl(rope2d_kernel<__half>, dim3(grid), dim3(256), 0, s, reinterpret_cast<__half*>(tokens), (int)B, (int)N, (int)H, (int)D, (long long)sB, (long long)sN, (long long)sH, p, base, fwd);
+  else if (dtype == 2) launch_pdl(rope2d_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, reinterpret_cast<__nv_bfloat16*>(tokens), (int)B, (int)N, (int)H, (int)D, (long long)sB, (long long)sN, (long long)sH, p, base, fwd);
   else return set_error("rope_2d: bad dtype %d", dtype);
   return check_launch("rope_2d");
 }
@@ -264,8 +278,8 @@ extern "C" int m3r_im2col16(const float* img, int32_t V, int32_t H, int32_t W, v
   if (!img || !out) return set_error("im2col16: null pointer");
   if (H % 16 || W % 16) return set_error("im2col16: image size (%d,%d) is not a multiple of the patch size 16", H, W);
   if (V <= 0) return 0;
-  im2col16_kernel<<<grid_for((long long)V * 3 * H * (W / 4), 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      img, V, H, W, reinterpret_cast<uint16_t*>(out), is_bf16);
+  launch_pdl(im2col16_kernel, dim3(grid_for((long long)V * 3 * H * (W / 4), 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             img, (int)V, (int)H, (int)W, reinterpret_cast<uint16_t*>(out), (int)is_bf16);
   return check_launch("im2col16");
 }
 
@@ -273,13 +287,13 @@ extern "C" int m3r_unpatchify(const float* proj, int32_t V, int32_t H, int32_t W
   if (!proj || !out) return set_error("unpatchify: null pointer");
   if (H % 16 || W % 16) return set_error("unpatchify: bad image size");
   if (V <= 0) return 0;
-  unpatchify_kernel<<<grid_for((long long)V * H * W, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(proj, V, H, W, C, out);
+  launch_pdl(unpatchify_kernel, dim3(grid_for((long long)V * H * W, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), proj, (int)V, (int)H, (int)W, (int)C, out);
   return check_launch("unpatchify");
 }
 
 extern "C" int m3r_postprocess(const float* pm, int64_t P, float* pts3d, float* pts3d_local, float* conf, void* stream) {
   if (!pm || !pts3d || !pts3d_local || !conf) return set_error("postprocess: null pointer");
   if (P <= 0) return 0;
-  postprocess_kernel<<<grid_for(P, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(pm, P, pts3d, pts3d_local, conf);
+  launch_pdl(postprocess_kernel, dim3(grid_for(P, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), pm, (long long)P, pts3d, pts3d_local, conf);
   return check_launch("postprocess");
 }

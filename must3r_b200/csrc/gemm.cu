@@ -82,6 +82,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();        // everything above overlapped the previous kernel's tail
+  griddep_launch();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -255,7 +257,8 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream) {
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {
     ProfScope prof(PROF_GEMM, 2.0 * a->M * (double)a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + (double)a->M * a->N * (a->out_dtype ? 2 : 4), stream);
-    gemm_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmW, p);
+    cudaError_t le = launch_pdl(gemm_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmW, p);
+    if (le != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(le));
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(e));

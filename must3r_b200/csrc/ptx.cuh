@@ -26,6 +26,14 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// Every kernel of this library is launched with programmaticStreamSerialization: it may start while its
+// predecessor in the stream is still draining.  griddep_wait() blocks until the predecessor grid has completed and
+// its memory is visible -- nothing before it may touch global memory written (or still read) by earlier kernels.
+// griddep_launch() lets the successor's CTAs begin their own prologue (barrier init, TMEM alloc, descriptor fetch).
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

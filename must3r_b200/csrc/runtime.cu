@@ -19,6 +19,12 @@ int set_error(const char* fmt, ...) {
   return 1;
 }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("M3R_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- profiling: a ring of event pairs; disabled by default (zero overhead beyond one branch)

@@ -178,7 +178,7 @@ def test_memory_cross_attention(dtype, Nm, n, N):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("qt,splits", [(1, 1), (1, 3), (1, 16), (2, 1)])
+@pytest.mark.parametrize("qt,splits", [(1, 1), (1, 3), (1, 16), (2, 1), (2, 2), (2, 7)])
 def test_attention_kernel_variants(dtype, qt, splits, monkeypatch):
     """Force each kernel configuration (1 or 2 query tiles per CTA, key-range splits + combine) on a masked,
     two-segment, ragged problem and on a long-key problem with large score spread (exercises the lazy rescale)."""

@@ -54,3 +54,21 @@ if "gemm" in which:
         out = torch.empty(M, N, device="cuda", dtype=dt)
         ms = timeit(lambda: ops.linear(a, w, None, out=out))
         print(f"gemm {name:14s} M={M:6d} N={N:5d} K={K:5d} {ms*1e3:9.1f} us  {2.0*M*N*K/ms/1e9 if ms else 0:8.1f} TFLOP/s", flush=True)
+
+if "sweep" in which:
+    shapes = {"update CA 1v M=10": (1, 12, 768, 7680), "update CA 1v M=19": (1, 12, 768, 14592), "update CA 1v M=3": (1, 12, 768, 2304),
+              "decoder SA 1v": (1, 12, 768, 768), "SA 224 1v": (1, 12, 196, 196), "CA 224 1v M=9": (1, 12, 196, 1764)}
+    for name, (B, H, Nq, Nk) in shapes.items():
+        D = H * 64
+        q = torch.randn(B * Nq, D, device="cuda").to(dt)
+        kv = torch.randn(B * Nk, 2 * D, device="cuda").to(dt)
+        res = []
+        for qt in (1, 2):
+            for sp in (1, 2, 3, 4, 6, 8, 12, 16):
+                os.environ["M3R_ATTN_QT"] = str(qt); os.environ["M3R_ATTN_SPLITS"] = str(sp)
+                ms = timeit(lambda: ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk), iters=7)
+                res.append((ms, qt, sp))
+        os.environ.pop("M3R_ATTN_QT"); os.environ.pop("M3R_ATTN_SPLITS")
+        ms0 = timeit(lambda: ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk), iters=7)
+        res.sort()
+        print(f"sweep {name:20s} default {ms0*1e3:7.1f} us | best " + "  ".join(f"qt{q_}s{s_}:{m*1e3:.1f}" for m, q_, s_ in res[:5]), flush=True)
