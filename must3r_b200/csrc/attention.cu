@@ -120,8 +120,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* v_empty = v_full + KS;     // [KS]
   uint64_t* s_full = v_empty + KS;     // [2][2] MMA -> softmax x : S_x(j) ready in buffer j&1
   uint64_t* p_full = s_full + 4;       // [2][2] softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
-  uint64_t* o_done = p_full + 4;       // [2]    MMA -> softmax x : P_x(j) V(j) accumulated into O_x
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* o_done = p_full + 4;       // [2][2] MMA -> softmax x : P_x(j) V(j) accumulated into O_x (one barrier per j&1:
+                                       //        a waiter that skips phases may only trust a parity wait on a barrier whose
+                                       //        previous phase is known to be complete)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
 
   const int warp = threadIdx.x >> 5;
   const int qblk = blockIdx.x, h = blockIdx.y;
@@ -146,8 +148,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (p.Nk1 > 0) { tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
     mbar_init(q_full, 1);
     for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); }
-    for (int s = 0; s < 2; ++s) mbar_init(&o_done[s], 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -214,7 +215,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             umma_ts(tmem_base + QT * 128 + x * 64, tmem_base + x * 128 + (j & 1) * 64 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv,
                     (j | k) ? 1u : 0u);
           }
-          umma_commit(&o_done[x]);
+          umma_commit(&o_done[x * 2 + (j & 1)]);
           if ((j & 1) && x == nqt - 1) umma_commit(&v_empty[st]);
         }
         __syncwarp();
@@ -290,8 +291,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           m_used = mx;
         }
         if (j > 0 && __any_sync(0xffffffffu, refresh)) {
-          // O_x *= alpha (per row).  P_x(j-1) V(j-1) must have landed first.
-          mbar_wait(&o_done[x], (j - 1) & 1);
+          // O_x *= alpha (per row).  P_x(j-1) V(j-1) (and, in order, everything before it) must have landed first.
+          // Phase (j-1)>>1 of barrier (j-1)&1: its previous phase, P V (j-3), completed before S(j) was committed.
+          mbar_wait(&o_done[x * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {               // rare path: small chunks keep the register footprint low
@@ -332,7 +334,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // ---- epilogue: wait for the last P V, normalise, store
     uint32_t accr[HD];
     if (j > 0) {
-      mbar_wait(&o_done[x], (j - 1) & 1);
+      mbar_wait(&o_done[x * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);      // last P V; MMAs complete in order
       tc_fence_after();
       tmem_ld32(o_addr, *reinterpret_cast<uint32_t(*)[32]>(&accr[0]));
       tmem_ld32(o_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&accr[32]));
@@ -467,17 +469,20 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     if (mk3(&tmV1, a->V1, a->ldk1, a->Nk1, a->kv_bstride1, Bkv)) return 1;
   } else { tmK1 = tmK0; tmV1 = tmV0; }
 
-  // ---- shape heuristics: 2 query tiles per CTA (shared K/V, ping-pong) whenever there is more than one tile of
-  // queries; when that leaves SMs idle (one view per step) the key range is split over several CTAs.
+  // ---- shape heuristics (tools/prof_attn.py sweep, profiles/r01_attention_sweep.txt):
+  //  * enough work for ~half a wave of 2-tile CTAs -> QT=2 (K/V tiles shared by two query tiles, ping-pong), no split;
+  //  * otherwise (one view per step) QT=1, two CTAs per SM, and the key range split so that ~2 CTAs per SM exist,
+  //    keeping at least 3 key tiles per split; a combine kernel merges the partial results.
   const int sms = num_sms();
   const int key_tiles = (a->Nk0 + AT_BN - 1) / AT_BN + (a->Nk1 + AT_BN - 1) / AT_BN;   // upper bound
-  int qt = a->Nq > 128 ? 2 : 1;
+  const int ctas2 = ((a->Nq + 255) / 256) * a->H * a->B;
+  const int ctas1 = ((a->Nq + 127) / 128) * a->H * a->B;
+  int qt = (a->Nq > 128 && 2 * ctas2 >= sms) ? 2 : 1;
   if (const char* f = getenv("M3R_ATTN_QT")) { const int v = atoi(f); if (v == 1 || v == 2) qt = v; }
-  const int ctas = ((a->Nq + qt * 128 - 1) / (qt * 128)) * a->H * a->B;
   int splits = 1;
-  if (ctas < sms) {
-    splits = (sms + ctas - 1) / ctas;
-    if (const char* f = getenv("M3R_ATTN_WAVES")) { const double wv = atof(f); if (wv > 0) splits = (int)((wv * sms + ctas - 1) / ctas); }
+  if (qt == 1 && ctas1 < 2 * sms) {
+    splits = (2 * sms + ctas1 / 2) / ctas1;
+    if (splits > key_tiles / 3) splits = key_tiles / 3;
   }
   if (const char* f = getenv("M3R_ATTN_SPLITS")) { const int v = atoi(f); if (v >= 1) splits = v; }
   if (splits > key_tiles) splits = key_tiles;
