@@ -10,7 +10,8 @@
 //                     tile j+1 is already in TMEM when the softmax of half tile j ends.
 //   warp 4*QT       : TMA producer -- Q tiles once, then K and V tiles (128 keys x 64) through mbarrier rings.
 //                     3-D tensor maps: rows beyond Nk read as zeros even inside over-allocated memory buffers.
-//   warp 4*QT+1     : TMEM allocator + single-thread MMA issuer:  S = Q K^T (both operands K-major smem),
+//   warps 4*QT+1..  : one single-thread MMA issuer per query tile (the first also allocates TMEM):
+//                     S = Q K^T (both operands K-major smem),
 //                     O += P V with P as the TMEM A operand and V as an MN-major smem B operand (V is consumed in
 //                     its natural [keys, d] layout -- no transpose anywhere in the pipeline).
 // O accumulates in TMEM across key tiles.  The running max used in the exponent is only refreshed when the true
@@ -37,7 +38,7 @@ constexpr float RESCALE_THRESHOLD = 8.0f;    // log2 units
 
 template <int QT> struct AttnCfg {
   static constexpr int KS = QT == 2 ? 3 : 2;                       // K / V ring depth
-  static constexpr int THREADS = 32 * (4 * QT + 2);
+  static constexpr int THREADS = 32 * (4 * QT + 1 + QT);          // softmax warpgroups + TMA warp + one MMA issuer per tile
   static constexpr int SMEM = (QT + 2 * KS) * TILE_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = QT == 2 ? 512 : 256;
 };
@@ -106,7 +107,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             const __grid_constant__ CUtensorMap tmV1, const AttnParams p) {
   using Cfg = AttnCfg<QT>;
   constexpr int KS = Cfg::KS;
-  constexpr int TMA_WARP = 4 * QT, MMA_WARP = 4 * QT + 1;
+  constexpr int TMA_WARP = 4 * QT, MMA_WARP = 4 * QT + 1;      // issuers: warps MMA_WARP .. MMA_WARP+QT-1
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // QT tiles
@@ -147,7 +148,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK0); tma_prefetch_desc(&tmV0);
     if (p.Nk1 > 0) { tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
     mbar_init(q_full, 1);
-    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], nqt); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], nqt); }
     for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
     fence_mbar_init();
   }
@@ -184,57 +185,54 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         ++i;
       }
     }
-  } else if (warp == MMA_WARP) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp >= MMA_WARP && warp < MMA_WARP + nqt) {
+    // ------------------------------------------------------------------ MMA issuer of query tile x (one thread)
+    // One issuer per query tile: the two softmax warpgroups progress independently (neither waits for the other's
+    // P), they only share the K / V stages, released when every issuer has committed its last read.
     constexpr uint32_t bf = BF16 ? 1u : 0u;
     constexpr uint32_t idesc_qk = make_idesc(AT_BM, 64, bf, 0, 0);      // S[128 x 64] = Q (K-major) * K_half^T (K-major)
     constexpr uint32_t idesc_pv = make_idesc(AT_BM, HD, bf, 0, 1);      // O[128 x 64] += P (TMEM)   * V_half (MN-major)
-    if (n_tiles > 0) {
+    const int x = warp - MMA_WARP;
+    if (n_tiles > 0 && (threadIdx.x & 31) == 0) {
       const int n_half = 2 * n_tiles;                            // half tiles of 64 keys
+      const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ + x * TILE_BYTES));
+      const uint64_t kdesc0 = smem_desc_sw128(smem_u32(sK));
+      const uint64_t vdesc0 = smem_desc_sw128(smem_u32(sV));
+      const uint32_t s_tmem = tmem_base + x * 128, o_tmem = tmem_base + QT * 128 + x * 64;
+      auto issue_qk = [&](int j) {                               // S_x[j&1] = Q_x K(j)^T ; K(j) = rows (j&1)*64.. of tile j/2
+        const int st = (j >> 1) % KS;
+        const uint64_t kdesc = kdesc0 + (uint64_t)((st * TILE_BYTES + (j & 1) * 64 * 128) >> 4);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) umma_ss(s_tmem + (j & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
+        umma_commit(&s_full[x * 2 + (j & 1)]);
+        if (j & 1) umma_commit(&k_empty[st]);                    // this issuer's last read of the K tile
+      };
+      auto issue_pv = [&](int j) {                               // O_x (+)= P_x(j) V(j)
+        const int st = (j >> 1) % KS;
+        const uint64_t vdesc = vdesc0 + (uint64_t)((st * TILE_BYTES + (j & 1) * 64 * 128) >> 4);
+#pragma unroll
+        for (int k = 0; k < 64 / 16; ++k) {
+          // 16 keys per MMA: P advances 8 TMEM columns (packed pairs), V advances 16 rows = 2048 B
+          umma_ts(o_tmem, s_tmem + (j & 1) * 64 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) ? 1u : 0u);
+        }
+        umma_commit(&o_done[x * 2 + (j & 1)]);
+        if (j & 1) umma_commit(&v_empty[st]);
+      };
       mbar_wait(q_full, 0);
-      tc_fence_after();
-      auto issue_qk = [&](int x, int j) {                        // S_x[j&1] = Q_x K(j)^T ; K(j) = rows (j&1)*64.. of tile j/2
-        const int t = j >> 1, st = t % KS;
-        if (elect_one()) {
-          const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ + x * TILE_BYTES));
-          const uint64_t kdesc = smem_desc_sw128(smem_u32(sK + st * TILE_BYTES + (j & 1) * 64 * 128));
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_ss(tmem_base + x * 128 + (j & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
-          umma_commit(&s_full[x * 2 + (j & 1)]);
-          if ((j & 1) && x == nqt - 1) umma_commit(&k_empty[st]);      // last reader of this K tile
-        }
-        __syncwarp();
-      };
-      auto issue_pv = [&](int x, int j) {                        // O_x (+)= P_x(j) V(j)
-        const int t = j >> 1, st = t % KS;
-        if (elect_one()) {
-          const uint64_t vdesc = smem_desc_sw128(smem_u32(sV + st * TILE_BYTES + (j & 1) * 64 * 128));
-#pragma unroll
-          for (int k = 0; k < 64 / 16; ++k) {
-            // 16 keys per MMA: P advances 8 TMEM columns (packed pairs), V advances 16 rows = 2048 B
-            umma_ts(tmem_base + QT * 128 + x * 64, tmem_base + x * 128 + (j & 1) * 64 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv,
-                    (j | k) ? 1u : 0u);
-          }
-          umma_commit(&o_done[x * 2 + (j & 1)]);
-          if ((j & 1) && x == nqt - 1) umma_commit(&v_empty[st]);
-        }
-        __syncwarp();
-      };
-      // prologue: the first two half tiles of every query tile
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      for (int j = 0; j < 2; ++j)
-        for (int x = 0; x < nqt; ++x) issue_qk(x, j);
+      issue_qk(0);
+      issue_qk(1);
       for (int j = 0; j < n_half; ++j) {
-        if ((j & 1) == 0) { mbar_wait(&v_full[(j >> 1) % KS], ((j >> 1) / KS) & 1); }
         const bool more = j + 2 < n_half;
-        if (more && (j & 1) == 0) { const int t2 = (j + 2) >> 1; mbar_wait(&k_full[t2 % KS], (t2 / KS) & 1); }
-        for (int x = 0; x < nqt; ++x) {
-          mbar_wait(&p_full[x * 2 + (j & 1)], (j >> 1) & 1);
-          tc_fence_after();
-          issue_pv(x, j);
-          if (more) issue_qk(x, j + 2);   // in-order tensor pipe: P V (j) has read P_x before buffer j&1 is rewritten
+        if ((j & 1) == 0) {
+          mbar_wait(&v_full[(j >> 1) % KS], ((j >> 1) / KS) & 1);
+          if (more) { const int t2 = (j + 2) >> 1; mbar_wait(&k_full[t2 % KS], (t2 / KS) & 1); }
         }
+        mbar_wait(&p_full[x * 2 + (j & 1)], (j >> 1) & 1);
+        tc_fence_after();
+        issue_pv(j);
+        if (more) issue_qk(j + 2);        // in-order tensor pipe: P V (j) has read P_x before buffer j&1 is rewritten
       }
     }
   } else if (warp < 4 * nqt) {

@@ -107,8 +107,34 @@ extern "C" int m3r_encoder_forward(const m3r_encoder_weights* w, const float* im
 // ------------------------------------------------------------------------------------------------ decoder
 namespace m3r {
 
+// Side stream for work that is independent of the main chain inside an update step (the K|V projection of the new
+// tokens, half of the post-feedback K|V rows): one-view steps launch kernels of <= 72..144 CTAs, so two of them fit
+// on the 148 SMs at once.  Fork / join with events; M3R_SIDE_STREAM=0 disables it.
+struct SideStream {
+  cudaStream_t s = nullptr, copy = nullptr;
+  cudaEvent_t ev[32];
+  int next = 0;
+  bool ok = false, enabled = true;
+  void init() {
+    if (ok || !enabled) return;
+    const char* e = getenv("M3R_SIDE_STREAM");
+    if (e && e[0] == '0') { enabled = false; return; }
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { enabled = false; return; }
+    if (cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking) != cudaSuccess) { enabled = false; return; }
+    for (int i = 0; i < 32; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    ok = true;
+  }
+  // make `to` wait for everything enqueued on `from` so far
+  void link(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = ev[next]; next = (next + 1) & 31;
+    cudaEventRecord(e, from);
+    cudaStreamWaitEvent(to, e, 0);
+  }
+};
+static SideStream g_side;
+
 struct DecWs {
-  uint16_t *enc16, *h16, *qkv16, *q16, *att16, *mlp16, *kvnew;
+  uint16_t *enc16, *h16, *h16b, *qkv16, *q16, *att16, *mlp16, *kvnew;
   float *x, *tmp, *snap, *off, *rope, *headout;
   int64_t M, Nt;
   std::vector<int64_t> row0;   // first row of each group
@@ -141,8 +167,9 @@ static int64_t dec_layout(const m3r_decoder_weights* w, const m3r_decoder_call* 
     ws->snap = a.take<float>((int64_t)w->depth * M * D);
     ws->off = a.take<float>(M * D);
     ws->kvnew = a.take<uint16_t>((int64_t)c->B * Nt * 2 * D);
+    ws->h16b = a.take<uint16_t>(M * D);
   } else {
-    ws->snap = nullptr; ws->off = nullptr; ws->kvnew = nullptr;
+    ws->snap = nullptr; ws->off = nullptr; ws->kvnew = nullptr; ws->h16b = nullptr;
   }
   return a.off + 256;
 }
@@ -173,6 +200,22 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   for (int g = 0; g < G; ++g) n_total += c->groups[g].n_views;
   // make_mem_mask rule (decoder.py:199-204, 291-296): skip own tokens unless rendering or a lone first image
   const bool use_skip = !c->render && (Nm > 0 || n_total > 1);
+  if (!c->render) g_side.init();
+  const bool side = !c->render && g_side.ok;
+  if (!c->render && Nm > 0 && !c->new_only) {
+    // old memory rows -> output memory tensors (the reference's torch.cat, decoder.py:330); independent of the whole
+    // step, so it runs on a copy stream and is joined at the end
+    cudaStream_t cps = side ? g_side.copy : cs;
+    if (side) g_side.link(cs, cps);
+    for (int l = 0; l < w->depth; ++l) {
+      if (!c->mem_out[l]) return set_error("decoder_forward: mem_out[%d] is null", l);
+      if (c->mem[l] == c->mem_out[l]) continue;
+      cudaError_t e = cudaMemcpy2DAsync(c->mem_out[l], (size_t)c->mem_out_bstride_rows * 2 * D * 2, c->mem[l],
+                                        (size_t)c->mem_bstride_rows * 2 * D * 2, (size_t)Nm * 2 * D * 2, B,
+                                        cudaMemcpyDeviceToDevice, cps);
+      if (e != cudaSuccess) return set_error("decoder_forward: memory copy failed: %s", cudaGetErrorString(e));
+    }
+  }
 
   // ---- prologue: projector + image2_embed, RoPE table (decoder.py:168-187, 272-289)
   for (int g = 0; g < G; ++g) {
@@ -199,13 +242,16 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
         xin = ws.snap;
       }
       xout = (l + 1 < w->depth) ? ws.snap + (int64_t)(l + 1) * M * D : ws.x;
-      // pre-feedback K|V of the new tokens -> second key segment (decoder.py:306, layers.py:81-88)
-      M3R_TRY(m3r_layernorm(xin, D, nullptr, 0, b.normy_w, b.normy_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+      // pre-feedback K|V of the new tokens -> second key segment (decoder.py:306, layers.py:81-88); independent of
+      // the self-attention branch until the cross-attention, so it runs on the side stream
+      void* kst = side ? (void*)g_side.s : stream;
+      if (side) g_side.link(cs, g_side.s);
+      M3R_TRY(m3r_layernorm(xin, D, nullptr, 0, b.normy_w, b.normy_b, w->ln_eps, M, D, ws.h16b, D, M3R_OUT_16, bf, kst));
       for (int g = 0; g < G; ++g) {
         const m3r_dec_group& gr = c->groups[g];
         const int Mg = B * gr.n_views * gr.N;
-        M3R_TRY(gemm(ws.h16 + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
-                     ws.kvnew + ws.tok0[g] * 2 * D, 2 * D, M3R_OUT_16, stream, nullptr, 0, 0, nullptr, 1, 0,
+        M3R_TRY(gemm(ws.h16b + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
+                     ws.kvnew + ws.tok0[g] * 2 * D, 2 * D, M3R_OUT_16, kst, nullptr, 0, 0, nullptr, 1, 0,
                      gr.n_views * gr.N, Nt));
       }
     } else {
@@ -231,6 +277,7 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     // ---- memory cross-attention (layers.py:92-97, attention.py:139-149): q = projq(LN2(x)), K|V = memory (+ new)
     M3R_TRY(m3r_layernorm(xt, D, nullptr, 0, b.norm2_w, b.norm2_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
     M3R_TRY(gemm(ws.h16, D, b.q_w, D, M, D, D, bf, b.q_b, 0, nullptr, 0, ws.q16, D, M3R_OUT_16, stream));
+    if (side && !c->render) g_side.link(g_side.s, cs);      // join: kvnew is ready
     for (int g = 0; g < G; ++g) {
       const m3r_dec_group& gr = c->groups[g];
       m3r_attn_args at = {};
@@ -257,6 +304,43 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     xcur = xout;
   }
 
+  // ---- feedback offset (feedback_mechanism.py:39-53): needed by the post-feedback K|V of every level but the last
+  const float* off = nullptr;
+  if (!c->render && w->feedback) {
+    const float* last = ws.snap + (int64_t)(w->depth - 1) * M * D;      // new_mem[-1] = input of the last block
+    M3R_TRY(m3r_layernorm(last, D, nullptr, 0, w->fbn_w, w->fbn_b, w->fb_ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+    if (w->feedback == 1) {
+      M3R_TRY(gemm(ws.h16, D, w->fb1_w, D, M, 4 * D, D, bf, w->fb1_b, M3R_ACT_GELU, nullptr, 0, ws.mlp16, 4 * D, M3R_OUT_16, stream));
+      M3R_TRY(gemm(ws.mlp16, 4 * D, w->fb2_w, 4 * D, M, D, 4 * D, bf, w->fb2_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, stream));
+    } else {
+      M3R_TRY(gemm(ws.h16, D, w->fb1_w, D, M, D, D, bf, w->fb1_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, stream));
+    }
+    off = ws.off;
+  }
+  // post-feedback K|V rows appended to the memory (decoder.py:323-330): levels [l0, l1) on stream `st`
+  auto post_feedback = [&](int l0, int l1, void* st, uint16_t* hbuf) -> int {
+    for (int l = l0; l < l1; ++l) {
+      const m3r_dec_block& b = w->blocks[l];
+      uint16_t* mo = reinterpret_cast<uint16_t*>(c->mem_out[l]);
+      if (!mo) return set_error("decoder_forward: mem_out[%d] is null", l);
+      const float* add = (off && l < w->depth - 1) ? off : nullptr;        // the last level gets no offset
+      M3R_TRY(m3r_layernorm(ws.snap + (int64_t)l * M * D, D, add, D, b.normy_w, b.normy_b, w->ln_eps, M, D, hbuf, D, M3R_OUT_16, bf, st));
+      for (int g = 0; g < G; ++g) {
+        const m3r_dec_group& gr = c->groups[g];
+        const int Mg = B * gr.n_views * gr.N;
+        M3R_TRY(gemm(hbuf + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
+                     mo + ((int64_t)(c->new_only ? 0 : Nm) + ws.tok0[g]) * 2 * D, 2 * D, M3R_OUT_16, st, nullptr, 0, 0, nullptr, 1, 0,
+                     gr.n_views * gr.N, c->mem_out_bstride_rows));
+      }
+    }
+    return 0;
+  };
+  const int l_split = side ? w->depth / 2 : 0;
+  if (!c->render && side) {
+    g_side.link(cs, g_side.s);                                 // fork: `off` and the snapshots are ready
+    M3R_TRY(post_feedback(0, l_split, g_side.s, ws.h16b));
+  }
+
   // ---- prediction head (decoder.py:149-156, head.py:69-72): LN -> Linear(768->1792) fp32 -> pixel shuffle
   M3R_TRY(m3r_layernorm(xcur, D, nullptr, 0, w->normd_w, w->normd_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
   M3R_TRY(gemm(ws.h16, D, w->head_w, D, M, w->out_dim, D, bf, w->head_b, 0, nullptr, 0, ws.headout, w->out_dim, M3R_OUT_F32, stream));
@@ -266,38 +350,10 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   }
 
   if (!c->render) {
-    // ---- feedback (feedback_mechanism.py:39-53) and post-feedback K|V appended to the memory (decoder.py:323-330)
-    const float* off = nullptr;
-    if (w->feedback) {
-      const float* last = ws.snap + (int64_t)(w->depth - 1) * M * D;      // new_mem[-1] = input of the last block
-      M3R_TRY(m3r_layernorm(last, D, nullptr, 0, w->fbn_w, w->fbn_b, w->fb_ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
-      if (w->feedback == 1) {
-        M3R_TRY(gemm(ws.h16, D, w->fb1_w, D, M, 4 * D, D, bf, w->fb1_b, M3R_ACT_GELU, nullptr, 0, ws.mlp16, 4 * D, M3R_OUT_16, stream));
-        M3R_TRY(gemm(ws.mlp16, 4 * D, w->fb2_w, 4 * D, M, D, 4 * D, bf, w->fb2_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, stream));
-      } else {
-        M3R_TRY(gemm(ws.h16, D, w->fb1_w, D, M, D, D, bf, w->fb1_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, stream));
-      }
-      off = ws.off;
-    }
-    for (int l = 0; l < w->depth; ++l) {
-      const m3r_dec_block& b = w->blocks[l];
-      uint16_t* mo = reinterpret_cast<uint16_t*>(c->mem_out[l]);
-      if (!mo) return set_error("decoder_forward: mem_out[%d] is null", l);
-      if (Nm > 0 && !c->new_only && c->mem[l] != c->mem_out[l]) {
-        cudaError_t e = cudaMemcpy2DAsync(mo, (size_t)c->mem_out_bstride_rows * 2 * D * 2, c->mem[l],
-                                          (size_t)c->mem_bstride_rows * 2 * D * 2, (size_t)Nm * 2 * D * 2, B,
-                                          cudaMemcpyDeviceToDevice, cs);
-        if (e != cudaSuccess) return set_error("decoder_forward: memory copy failed: %s", cudaGetErrorString(e));
-      }
-      const float* add = (off && l < w->depth - 1) ? off : nullptr;        // the last level gets no offset
-      M3R_TRY(m3r_layernorm(ws.snap + (int64_t)l * M * D, D, add, D, b.normy_w, b.normy_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
-      for (int g = 0; g < G; ++g) {
-        const m3r_dec_group& gr = c->groups[g];
-        const int Mg = B * gr.n_views * gr.N;
-        M3R_TRY(gemm(ws.h16 + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
-                     mo + ((int64_t)(c->new_only ? 0 : Nm) + ws.tok0[g]) * 2 * D, 2 * D, M3R_OUT_16, stream, nullptr, 0, 0, nullptr, 1, 0,
-                     gr.n_views * gr.N, c->mem_out_bstride_rows));
-      }
+    M3R_TRY(post_feedback(l_split, w->depth, stream, ws.h16));
+    if (side) {
+      g_side.link(g_side.s, cs);                               // join the side stream
+      if (Nm > 0 && !c->new_only) g_side.link(g_side.copy, cs);  // and the old-memory copies
     }
   }
   return 0;
