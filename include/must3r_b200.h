@@ -34,8 +34,9 @@ int m3r_abi_version(void);
 long long m3r_launch_count(void);
 /* Optional per-kernel device timing for bench.py: CUDA events are recorded on the launch stream around every
  * GEMM / attention / LayerNorm kernel while enabled.  m3r_prof_read synchronises and fills
- * out[cat*4 + {0: ms, 1: launches, 2: algorithmic flops, 3: algorithmic bytes}], cat 0 gemm, 1 attention,
- * 2 layernorm, 3 other (16 doubles). */
+ * out[cat*4 + {0: ms, 1: launches, 2: algorithmic flops, 3: algorithmic bytes}] for the 7 categories
+ * gemm_kernel<256>, gemm_kernel<128>, gemm_kernel<64>, attn_kernel<QT=2>, attn_kernel<QT=1> (+combine), layernorm,
+ * other (28 doubles). */
 void m3r_prof_enable(int on);
 int m3r_prof_read(double* out);
 

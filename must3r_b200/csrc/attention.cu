@@ -17,7 +17,7 @@
 // O accumulates in TMEM across key tiles.  The running max used in the exponent is only refreshed when the true
 // row max grew by more than 2^8 (lazy rescaling): the rare refresh multiplies O in TMEM by the correction factor;
 // the final O / l is mathematically unchanged.
-// TMEM columns (QT=2): S_A0 [0,64) S_A1 [64,128) S_B0 [128,192) S_B1 [192,256) O_A [256,320) O_B [320,384);
+// TMEM columns (QT=2): S_A0..2 [0,192) S_B0..2 [192,384) O_A [384,448) O_B [448,512)  (QT=1: S [0,192), O [192,256));
 // P_x(j) (packed 16-bit pairs, 32 columns) aliases the first half of the S buffer it was computed from.
 //
 // Keys come from two segments (stored memory + this step's new tokens) so the reference's torch.cat of the memory
@@ -35,6 +35,7 @@ constexpr int AT_BN = 128;
 constexpr int HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB
 constexpr float RESCALE_THRESHOLD = 8.0f;    // log2 units
+constexpr int NSB = 3;                       // S buffers (64 columns each) per query tile: Q K^T runs up to 3 half tiles ahead
 
 template <int QT> struct AttnCfg {
   static constexpr int KS = QT == 2 ? 3 : 2;                       // K / V ring depth
@@ -119,12 +120,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* k_empty = k_full + KS;     // [KS]
   uint64_t* v_full = k_empty + KS;     // [KS]
   uint64_t* v_empty = v_full + KS;     // [KS]
-  uint64_t* s_full = v_empty + KS;     // [2][2] MMA -> softmax x : S_x(j) ready in buffer j&1
-  uint64_t* p_full = s_full + 4;       // [2][2] softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
-  uint64_t* o_done = p_full + 4;       // [2][2] MMA -> softmax x : P_x(j) V(j) accumulated into O_x (one barrier per j&1:
-                                       //        a waiter that skips phases may only trust a parity wait on a barrier whose
-                                       //        previous phase is known to be complete)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 4);
+  uint64_t* s_full = v_empty + KS;       // [2][NSB] MMA -> softmax x : S_x(j) ready in buffer j%NSB
+  uint64_t* p_full = s_full + 2 * NSB;   // [2][NSB] softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
+  uint64_t* o_done = p_full + 2 * NSB;   // [2][NSB] MMA -> softmax x : P_x(j) V(j) accumulated into O_x (one barrier per
+                                         //          buffer: a waiter that skips phases may only trust a parity wait on a
+                                         //          barrier whose previous phase is known to be complete)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2 * NSB);
 
   const int warp = threadIdx.x >> 5;
   const int qblk = blockIdx.x, h = blockIdx.y;
@@ -149,7 +150,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (p.Nk1 > 0) { tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
     mbar_init(q_full, 1);
     for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], nqt); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], nqt); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
+    for (int s = 0; s < 2 * NSB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -198,41 +199,41 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ + x * TILE_BYTES));
       const uint64_t kdesc0 = smem_desc_sw128(smem_u32(sK));
       const uint64_t vdesc0 = smem_desc_sw128(smem_u32(sV));
-      const uint32_t s_tmem = tmem_base + x * 128, o_tmem = tmem_base + QT * 128 + x * 64;
-      auto issue_qk = [&](int j) {                               // S_x[j&1] = Q_x K(j)^T ; K(j) = rows (j&1)*64.. of tile j/2
-        const int st = (j >> 1) % KS;
+      const uint32_t s_tmem = tmem_base + x * (NSB * 64), o_tmem = tmem_base + QT * (NSB * 64) + x * 64;
+      auto issue_qk = [&](int j) {                               // S_x[j%NSB] = Q_x K(j)^T ; K(j) = rows (j&1)*64.. of tile j/2
+        const int st = (j >> 1) % KS, sb = j % NSB;
         const uint64_t kdesc = kdesc0 + (uint64_t)((st * TILE_BYTES + (j & 1) * 64 * 128) >> 4);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(s_tmem + (j & 1) * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
-        umma_commit(&s_full[x * 2 + (j & 1)]);
+        for (int k = 0; k < HD / 16; ++k) umma_ss(s_tmem + sb * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
+        umma_commit(&s_full[x * NSB + sb]);
         if (j & 1) umma_commit(&k_empty[st]);                    // this issuer's last read of the K tile
       };
       auto issue_pv = [&](int j) {                               // O_x (+)= P_x(j) V(j)
-        const int st = (j >> 1) % KS;
+        const int st = (j >> 1) % KS, sb = j % NSB;
         const uint64_t vdesc = vdesc0 + (uint64_t)((st * TILE_BYTES + (j & 1) * 64 * 128) >> 4);
 #pragma unroll
         for (int k = 0; k < 64 / 16; ++k) {
           // 16 keys per MMA: P advances 8 TMEM columns (packed pairs), V advances 16 rows = 2048 B
-          umma_ts(o_tmem, s_tmem + (j & 1) * 64 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) ? 1u : 0u);
+          umma_ts(o_tmem, s_tmem + sb * 64 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) ? 1u : 0u);
         }
-        umma_commit(&o_done[x * 2 + (j & 1)]);
+        umma_commit(&o_done[x * NSB + sb]);
         if (j & 1) umma_commit(&v_empty[st]);
       };
+      auto wait_k = [&](int t) { mbar_wait(&k_full[t % KS], (t / KS) & 1); };
       mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
+      wait_k(0);
       tc_fence_after();
       issue_qk(0);
       issue_qk(1);
+      if (n_half > 2) { wait_k(1); tc_fence_after(); issue_qk(2); }
       for (int j = 0; j < n_half; ++j) {
-        const bool more = j + 2 < n_half;
-        if ((j & 1) == 0) {
-          mbar_wait(&v_full[(j >> 1) % KS], ((j >> 1) / KS) & 1);
-          if (more) { const int t2 = (j + 2) >> 1; mbar_wait(&k_full[t2 % KS], (t2 / KS) & 1); }
-        }
-        mbar_wait(&p_full[x * 2 + (j & 1)], (j >> 1) & 1);
+        const bool more = j + NSB < n_half;
+        if ((j & 1) == 0) mbar_wait(&v_full[(j >> 1) % KS], ((j >> 1) / KS) & 1);
+        if (more && ((j + NSB) & 1) == 0) wait_k((j + NSB) >> 1);       // first use of that K tile
+        mbar_wait(&p_full[x * NSB + j % NSB], (j / NSB) & 1);
         tc_fence_after();
         issue_pv(j);
-        if (more) issue_qk(j + 2);        // in-order tensor pipe: P V (j) has read P_x before buffer j&1 is rewritten
+        if (more) issue_qk(j + NSB);      // in-order tensor pipe: P V (j) has read P_x before its buffer is rewritten
       }
     }
   } else if (warp < 4 * nqt) {
@@ -243,8 +244,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int row = quarter * 32 + lane;
     const int q_idx = q0 + x * AT_BM + row;
     const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
-    const uint32_t s_addr = lane_addr + x * 128;
-    const uint32_t o_addr = lane_addr + QT * 128 + x * 64;
+    const uint32_t s_addr = lane_addr + x * (NSB * 64);
+    const uint32_t o_addr = lane_addr + QT * (NSB * 64) + x * 64;
     float m_used = -INFINITY;      // max currently folded into the exponent (raw score units)
     float l_run = 0.f;
 
@@ -256,8 +257,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       ++i;
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh, ++j) {
-        const int buf = j & 1;
-        mbar_wait(&s_full[x * 2 + buf], (j >> 1) & 1);
+        const int buf = j % NSB;
+        mbar_wait(&s_full[x * NSB + buf], (j / NSB) & 1);
         tc_fence_after();
         uint32_t raw[64];
         tmem_ld32(s_addr + buf * 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
@@ -290,8 +291,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
         if (j > 0 && __any_sync(0xffffffffu, refresh)) {
           // O_x *= alpha (per row).  P_x(j-1) V(j-1) (and, in order, everything before it) must have landed first.
-          // Phase (j-1)>>1 of barrier (j-1)&1: its previous phase, P V (j-3), completed before S(j) was committed.
-          mbar_wait(&o_done[x * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);
+          // Phase (j-1)/NSB of barrier (j-1)%NSB: its previous phase, P V (j-1-NSB), completed before S(j) was committed
+          // (Q K^T (j) is issued right after P V (j-NSB)).
+          mbar_wait(&o_done[x * NSB + (j - 1) % NSB], ((j - 1) / NSB) & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {               // rare path: small chunks keep the register footprint low
@@ -324,7 +326,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         }
         tmem_wait_st();
         tc_fence_before();
-        mbar_arrive(&p_full[x * 2 + buf]);
+        mbar_arrive(&p_full[x * NSB + buf]);
         l_run += (r0 + r1) + (r2 + r3);
       }
     }
@@ -332,7 +334,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // ---- epilogue: wait for the last P V, normalise, store
     uint32_t accr[HD];
     if (j > 0) {
-      mbar_wait(&o_done[x * 2 + ((j - 1) & 1)], ((j - 1) >> 1) & 1);      // last P V; MMAs complete in order
+      mbar_wait(&o_done[x * NSB + (j - 1) % NSB], ((j - 1) / NSB) & 1);      // last P V; MMAs complete in order
       tc_fence_after();
       tmem_ld32(o_addr, *reinterpret_cast<uint32_t(*)[32]>(&accr[0]));
       tmem_ld32(o_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&accr[32]));
@@ -507,7 +509,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   }
   {
     const double nk_eff = (double)(a->Nk0 + a->Nk1 - a->skip_len);
-    ProfScope prof(PROF_ATTN, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
+    ProfScope prof(qt == 2 ? PROF_ATTN_QT2 : PROF_ATTN_QT1, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
                    2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)Bkv * (a->Nk0 + a->Nk1) * a->H * HD * 2), cs);
     int rc;
     if (a->is_bf16) rc = qt == 2 ? launch_attn<true, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) : launch_attn<true, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs);

@@ -256,7 +256,7 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream) {
   const int tiles = ((a->M + BM - 1) / BM) * (a->N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
   {
-    ProfScope prof(PROF_GEMM, 2.0 * a->M * (double)a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + (double)a->M * a->N * (a->out_dtype ? 2 : 4), stream);
+    ProfScope prof(BN == 256 ? PROF_GEMM256 : (BN == 128 ? PROF_GEMM128 : PROF_GEMM64), 2.0 * a->M * (double)a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + (double)a->M * a->N * (a->out_dtype ? 2 : 4), stream);
     cudaError_t le = launch_pdl(gemm_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmW, p);
     if (le != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(le));
   }

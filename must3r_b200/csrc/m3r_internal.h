@@ -13,7 +13,7 @@ int num_sms();                                  // SM count of the current devic
 void count_launch();                            // bumps the kernel-launch counter (m3r_launch_count)
 
 // Optional per-category device timing (m3r_prof_*): CUDA events recorded on the launch stream around each kernel.
-enum ProfCat { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_OTHER = 3, PROF_NCAT = 4 };
+enum ProfCat { PROF_GEMM256 = 0, PROF_GEMM128 = 1, PROF_GEMM64 = 2, PROF_ATTN_QT2 = 3, PROF_ATTN_QT1 = 4, PROF_LN = 5, PROF_OTHER = 6, PROF_NCAT = 7 };
 struct ProfScope {
   int slot;
   ProfScope(int cat, double flops, double bytes, cudaStream_t s);

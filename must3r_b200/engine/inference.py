@@ -20,6 +20,28 @@ import torch
 from ..model.common import ActivationType
 
 
+# --------------------------------------------------------------------------------------------- host copies
+_PENDING_HOST_COPIES = [False]
+
+
+def _to_out(v, outdevice):
+    """`.to(outdevice)` of the reference (engine/inference.py:196), except that device->host results go through pinned
+    staging buffers with an asynchronous copy, so the D2H traffic overlaps the next decoder steps instead of stalling
+    the launch thread.  `_sync_host_copies()` is called before results are handed to any callback or returned."""
+    if v.is_cuda and str(outdevice) == "cpu":
+        dst = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
+        dst.copy_(v, non_blocking=True)
+        _PENDING_HOST_COPIES[0] = True
+        return dst
+    return v.to(outdevice)
+
+
+def _sync_host_copies():
+    if _PENDING_HOST_COPIES[0]:
+        torch.cuda.current_stream().synchronize()
+        _PENDING_HOST_COPIES[0] = False
+
+
 # --------------------------------------------------------------------------------------------- postprocess
 def _act(xyz, activation):
     if isinstance(activation, str):
@@ -130,8 +152,9 @@ def encoder_multi_ar(encoder, imgs, true_shape, verbose=False, max_bs=None, devi
     for im, ts, idx in zip(img_stacks, shape_stacks, index_stacks):
         xs, ps = encoder(im.to(device), ts.to(device))
         for j, view in enumerate(idx):
-            x[view] = xs[j].to(outdevice)
-            pos[view] = ps[j].to(outdevice)
+            x[view] = _to_out(xs[j], outdevice)
+            pos[view] = _to_out(ps[j], outdevice)
+    _sync_host_copies()
     return x, pos
 
 
@@ -156,9 +179,9 @@ def inference_multi_ar_batch(encoder, decoder, imgs, true_shape, mem=None, verbo
     for pm in pms:
         pm = pm.squeeze(0)
         if post_process_function is not None:
-            pm = {k: v.to(outdevice) for k, v in post_process_function(pm).items()}
+            pm = {k: _to_out(v, outdevice) for k, v in post_process_function(pm).items()}
         else:
-            pm = pm.to(outdevice)
+            pm = _to_out(pm, outdevice)
         results.append(pm)
     return mem, results
 
@@ -197,15 +220,25 @@ def _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device):
     return xi, pi
 
 
+def _default_is_keyframe(id, res, scene_state):
+    return id % 3 == 0
+
+
+def _default_scene_state_update(res, scene_state):
+    return scene_state
+
+
 # --------------------------------------------------------------------------------------------- video / rolling window
 @torch.no_grad()
 def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, verbose=False, max_bs=None,
                              encoder_precomputed_features=None, preserve_gpu_mem=False,
                              post_process_function=lambda x: {'pts3d': x}, device=None, return_mem=False,
                              viser_server=None, num_refinements_iterations=0, local_context_size=25,
-                             is_keyframe_function=lambda id, res, scene_state: (id % 3 == 0),
-                             scene_state=None, scene_state_update_function=lambda res, scene_state: scene_state):
-    """Streaming schedule with keyframes and a rolling window of recent frames (engine/inference.py:231-366)."""
+                             is_keyframe_function=None, scene_state=None, scene_state_update_function=None):
+    """Streaming schedule with keyframes and a rolling window of recent frames (engine/inference.py:231-366).
+    Default callbacks as in the reference: keyframe iff id % 3 == 0 (:236), scene state passed through (:237)."""
+    is_keyframe_function = is_keyframe_function or _default_is_keyframe
+    scene_state_update_function = scene_state_update_function or _default_scene_state_update
     true_shape = torch.stack(true_shape, dim=0)
     n = true_shape.shape[0]
     device = device or true_shape.device
@@ -214,6 +247,8 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
     first_pass = [None] * bounds[-1]
     mem = None
     label_of, keyframes = {}, set()
+    custom_callbacks = (viser_server is not None or is_keyframe_function is not _default_is_keyframe
+                        or scene_state_update_function is not _default_scene_state_update)
     window = deque()
     for _ in range(num_refinements_iterations + 1):
         window = deque()
@@ -232,6 +267,8 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
             first_pass[lo:hi] = res
             mem = list(new_mem)
             new_labels = _fresh_labels(mem, n_before)
+            if custom_callbacks:
+                _sync_host_copies()        # user callbacks may read the (host) results
             flags = []
             if not label_of:                       # initialisation: every view is a keyframe
                 for j, vid in enumerate(ids_i):
@@ -270,6 +307,7 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
             gone = window.popleft()
             if gone not in keyframes:
                 mem[0], mem[1] = _remove_from_mem(mem[0], mem[1], label_of[gone])
+    _sync_host_copies()
     return (mem, first_pass) if return_mem else first_pass
 
 
@@ -320,6 +358,7 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
                 res = unstack_pointmaps(idx_st, res)
                 first_pass[lo:hi] = res
                 if viser_server is not None:
+                    _sync_host_copies()
                     viser_server.set_views(ids_i, imgs_i, res, [True] * len(imgs_i))
     else:
         first_pass, mem = None, precomputed_mem
@@ -331,6 +370,7 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
         n = len(x)
     assert mem is not None
     if n == 0:
+        _sync_host_copies()
         return (mem, first_pass, []) if return_mem else (first_pass, [])
 
     ts_st, idx_st, x_st, pos_st, img_st, id_st = stack_views(true_shape, [x, pos, imgs, img_ids], max_bs=max_bs)
@@ -343,10 +383,12 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
                                           viser_server=viser_server)
         rendered.append(out[0])
         if viser_server is not None:
+            _sync_host_copies()
             tmp = unstack_pointmaps([torch.arange(ids.shape[0])], out)
             for i in range(ids.shape[0]):
                 viser_server.set_views([ids[i]], [ims[i]], [tmp[i]])
     pointmaps = unstack_pointmaps(idx_st, rendered)
+    _sync_host_copies()
     return (mem, first_pass, pointmaps) if return_mem else (first_pass, pointmaps)
 
 
