@@ -4,10 +4,10 @@
 // share every K / V tile that TMA brings in (half the L2->smem traffic) and ping-pong on the tensor pipe, so one
 // tile's softmax overlaps the other's MMAs.  Roles:
 //   warps 0..4*QT-1 : softmax warpgroup per query tile -- ONE query row per thread (TMEM lane == row, so row max /
-//                     row sum need no shuffles); keys are consumed in half tiles of 64: single pass over the 64
-//                     scores held in registers: row max, exp2 with the scale folded in, row sum, pack P to 16-bit
-//                     and store it over S's own TMEM columns.  S is double-buffered per warpgroup so Q K^T of half
-//                     tile j+1 is already in TMEM when the softmax of half tile j ends.
+//                     row sum need no shuffles); single pass over a 128-key S row held in registers: row max, exp2
+//                     with the scale folded in, row sum, pack P to 16-bit into its own TMEM columns.  As soon as
+//                     the row is in registers the S columns are handed back, so Q K^T of tile j+1 runs under the
+//                     exponentials of tile j.
 //   warp 4*QT       : TMA producer -- Q tiles once, then K and V tiles (128 keys x 64) through mbarrier rings.
 //                     3-D tensor maps: rows beyond Nk read as zeros even inside over-allocated memory buffers.
 //   warps 4*QT+1..  : one single-thread MMA issuer per query tile (the first also allocates TMEM):
@@ -17,8 +17,7 @@
 // O accumulates in TMEM across key tiles.  The running max used in the exponent is only refreshed when the true
 // row max grew by more than 2^8 (lazy rescaling): the rare refresh multiplies O in TMEM by the correction factor;
 // the final O / l is mathematically unchanged.
-// TMEM columns (QT=2): S_A0..2 [0,192) S_B0..2 [192,384) O_A [384,448) O_B [448,512)  (QT=1: S [0,192), O [192,256));
-// P_x(j) (packed 16-bit pairs, 32 columns) aliases the first half of the S buffer it was computed from.
+// TMEM columns per query tile x (256 each): S [0,128)  P [128,192) (packed 16-bit pairs)  O [192,256).
 //
 // Keys come from two segments (stored memory + this step's new tokens) so the reference's torch.cat of the memory
 // (decoder.py:306) never happens; a per-batch skip range implements make_mem_mask (decoder.py:119-139): fully
@@ -35,7 +34,6 @@ constexpr int AT_BN = 128;
 constexpr int HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB
 constexpr float RESCALE_THRESHOLD = 8.0f;    // log2 units
-constexpr int NSB = 3;                       // S buffers (64 columns each) per query tile: Q K^T runs up to 3 half tiles ahead
 
 template <int QT> struct AttnCfg {
   static constexpr int KS = QT == 2 ? 3 : 2;                       // K / V ring depth
@@ -102,7 +100,7 @@ template <bool BF16> __device__ __forceinline__ uint32_t packp(float lo, float h
 }
 
 template <bool BF16, int QT>
-__global__ void __launch_bounds__(AttnCfg<QT>::THREADS, 1)
+__global__ void __launch_bounds__(AttnCfg<QT>::THREADS, QT == 1 ? 2 : 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
             const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
             const __grid_constant__ CUtensorMap tmV1, const AttnParams p) {
@@ -120,12 +118,11 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* k_empty = k_full + KS;     // [KS]
   uint64_t* v_full = k_empty + KS;     // [KS]
   uint64_t* v_empty = v_full + KS;     // [KS]
-  uint64_t* s_full = v_empty + KS;       // [2][NSB] MMA -> softmax x : S_x(j) ready in buffer j%NSB
-  uint64_t* p_full = s_full + 2 * NSB;   // [2][NSB] softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
-  uint64_t* o_done = p_full + 2 * NSB;   // [2][NSB] MMA -> softmax x : P_x(j) V(j) accumulated into O_x (one barrier per
-                                         //          buffer: a waiter that skips phases may only trust a parity wait on a
-                                         //          barrier whose previous phase is known to be complete)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2 * NSB);
+  uint64_t* s_full = v_empty + KS;     // [2] MMA -> softmax x : S_x(j) ready
+  uint64_t* s_free = s_full + 2;       // [2] softmax x -> MMA : S_x(j) is in registers, the columns may be overwritten
+  uint64_t* p_full = s_free + 2;       // [2] softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
+  uint64_t* o_done = p_full + 2;       // [2] MMA -> softmax x : P_x(j) V(j) accumulated into O_x, P columns free again
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int qblk = blockIdx.x, h = blockIdx.y;
@@ -150,7 +147,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (p.Nk1 > 0) { tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
     mbar_init(q_full, 1);
     for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], nqt); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], nqt); }
-    for (int s = 0; s < 2 * NSB; ++s) { mbar_init(&s_full[s], 1); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -191,49 +188,48 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     // One issuer per query tile: the two softmax warpgroups progress independently (neither waits for the other's
     // P), they only share the K / V stages, released when every issuer has committed its last read.
     constexpr uint32_t bf = BF16 ? 1u : 0u;
-    constexpr uint32_t idesc_qk = make_idesc(AT_BM, 64, bf, 0, 0);      // S[128 x 64] = Q (K-major) * K_half^T (K-major)
-    constexpr uint32_t idesc_pv = make_idesc(AT_BM, HD, bf, 0, 1);      // O[128 x 64] += P (TMEM)   * V_half (MN-major)
+    constexpr uint32_t idesc_qk = make_idesc(AT_BM, AT_BN, bf, 0, 0);   // S[128 x 128] = Q (K-major) * K^T (K-major)
+    constexpr uint32_t idesc_pv = make_idesc(AT_BM, HD, bf, 0, 1);      // O[128 x 64] += P (TMEM)   * V (MN-major)
     const int x = warp - MMA_WARP;
     if (n_tiles > 0 && (threadIdx.x & 31) == 0) {
-      const int n_half = 2 * n_tiles;                            // half tiles of 64 keys
       const uint64_t qdesc = smem_desc_sw128(smem_u32(sQ + x * TILE_BYTES));
       const uint64_t kdesc0 = smem_desc_sw128(smem_u32(sK));
       const uint64_t vdesc0 = smem_desc_sw128(smem_u32(sV));
-      const uint32_t s_tmem = tmem_base + x * (NSB * 64), o_tmem = tmem_base + QT * (NSB * 64) + x * 64;
-      auto issue_qk = [&](int j) {                               // S_x[j%NSB] = Q_x K(j)^T ; K(j) = rows (j&1)*64.. of tile j/2
-        const int st = (j >> 1) % KS, sb = j % NSB;
-        const uint64_t kdesc = kdesc0 + (uint64_t)((st * TILE_BYTES + (j & 1) * 64 * 128) >> 4);
+      const uint32_t s_tmem = tmem_base + x * 256, p_tmem = s_tmem + 128, o_tmem = s_tmem + 192;
+      auto issue_qk = [&](int j) {                               // S_x = Q_x K(j)^T
+        const int st = j % KS;
+        const uint64_t kdesc = kdesc0 + (uint64_t)((st * TILE_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(s_tmem + sb * 64, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
-        umma_commit(&s_full[x * NSB + sb]);
-        if (j & 1) umma_commit(&k_empty[st]);                    // this issuer's last read of the K tile
+        for (int k = 0; k < HD / 16; ++k) umma_ss(s_tmem, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k ? 1u : 0u);
+        umma_commit(&s_full[x]);
+        umma_commit(&k_empty[st]);                               // this issuer's only read of the K tile
       };
       auto issue_pv = [&](int j) {                               // O_x (+)= P_x(j) V(j)
-        const int st = (j >> 1) % KS, sb = j % NSB;
-        const uint64_t vdesc = vdesc0 + (uint64_t)((st * TILE_BYTES + (j & 1) * 64 * 128) >> 4);
+        const int st = j % KS;
+        const uint64_t vdesc = vdesc0 + (uint64_t)((st * TILE_BYTES) >> 4);
 #pragma unroll
-        for (int k = 0; k < 64 / 16; ++k) {
+        for (int k = 0; k < AT_BN / 16; ++k) {
           // 16 keys per MMA: P advances 8 TMEM columns (packed pairs), V advances 16 rows = 2048 B
-          umma_ts(o_tmem, s_tmem + sb * 64 + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) ? 1u : 0u);
+          umma_ts(o_tmem, p_tmem + k * 8, vdesc + (uint64_t)(k * 128), idesc_pv, (j | k) ? 1u : 0u);
         }
-        umma_commit(&o_done[x * NSB + sb]);
-        if (j & 1) umma_commit(&v_empty[st]);
+        umma_commit(&o_done[x]);
+        umma_commit(&v_empty[st]);
       };
-      auto wait_k = [&](int t) { mbar_wait(&k_full[t % KS], (t / KS) & 1); };
       mbar_wait(q_full, 0);
-      wait_k(0);
+      mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_qk(0);
-      issue_qk(1);
-      if (n_half > 2) { wait_k(1); tc_fence_after(); issue_qk(2); }
-      for (int j = 0; j < n_half; ++j) {
-        const bool more = j + NSB < n_half;
-        if ((j & 1) == 0) mbar_wait(&v_full[(j >> 1) % KS], ((j >> 1) / KS) & 1);
-        if (more && ((j + NSB) & 1) == 0) wait_k((j + NSB) >> 1);       // first use of that K tile
-        mbar_wait(&p_full[x * NSB + j % NSB], (j / NSB) & 1);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) {
+          mbar_wait(&k_full[(j + 1) % KS], ((j + 1) / KS) & 1);
+          mbar_wait(&s_free[x], j & 1);                          // softmax holds S(j) in registers
+          tc_fence_after();
+          issue_qk(j + 1);                                       // runs under the exponentials of tile j
+        }
+        mbar_wait(&v_full[j % KS], (j / KS) & 1);
+        mbar_wait(&p_full[x], j & 1);
         tc_fence_after();
         issue_pv(j);
-        if (more) issue_qk(j + NSB);      // in-order tensor pipe: P V (j) has read P_x before its buffer is rewritten
       }
     }
   } else if (warp < 4 * nqt) {
@@ -244,57 +240,59 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const int row = quarter * 32 + lane;
     const int q_idx = q0 + x * AT_BM + row;
     const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
-    const uint32_t s_addr = lane_addr + x * (NSB * 64);
-    const uint32_t o_addr = lane_addr + QT * (NSB * 64) + x * 64;
+    const uint32_t s_addr = lane_addr + x * 256;
+    const uint32_t p_addr = s_addr + 128;
+    const uint32_t o_addr = s_addr + 192;
     float m_used = -INFINITY;      // max currently folded into the exponent (raw score units)
     float l_run = 0.f;
 
     TileWalk walk(p.Nk0, p.Nk1, lo, hi);
     TileIt it;
-    int i = 0, j = 0;                 // j counts half tiles of 64 keys
+    int i = 0, j = 0;
     while (walk.next(it)) {
       if (i < i0 || i >= i1) { ++i; continue; }
       ++i;
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh, ++j) {
-        const int buf = j % NSB;
-        mbar_wait(&s_full[x * NSB + buf], (j / NSB) & 1);
+      mbar_wait(&s_full[x], j & 1);
+      tc_fence_after();
+      uint32_t raw[128];
+      tmem_ld32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
+      tmem_ld32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
+      tmem_ld32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[64]));
+      tmem_ld32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&raw[96]));
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&s_free[x]);                     // Q K^T of the next tile may overwrite S now
+      if (it.mask) {
+#pragma unroll
+        for (int c = 0; c < 128; ++c) {
+          const int g = it.g0 + c;
+          const bool ok = c < it.nvalid && !(g >= lo && g < hi);
+          if (!ok) raw[c] = 0xff800000u;            // -inf
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(raw[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(raw[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(raw[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(raw[c + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // lazy rescaling: refresh the folded max only when it is stale by more than 2^8
+      float alpha = 1.f;
+      bool refresh = false;
+      if (mx > -INFINITY && (m_used == -INFINITY || (mx - m_used) * p.sl2 > RESCALE_THRESHOLD)) {
+        refresh = true;
+        alpha = (m_used == -INFINITY) ? 0.f : ex2((m_used - mx) * p.sl2);
+        m_used = mx;
+      }
+      if (j > 0) {
+        // P V (j-1) must have consumed the P columns (and landed in O) before they are rewritten / O is rescaled.
+        // Every phase of o_done is waited for, in order, so the parity wait is exact.
+        mbar_wait(&o_done[x], (j - 1) & 1);
         tc_fence_after();
-        uint32_t raw[64];
-        tmem_ld32(s_addr + buf * 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
-        tmem_ld32(s_addr + buf * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
-        tmem_wait_ld();
-        if (it.mask) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const int col = hh * 64 + c, g = it.g0 + col;
-            const bool ok = col < it.nvalid && !(g >= lo && g < hi);
-            if (!ok) raw[c] = 0xff800000u;            // -inf
-          }
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 64; c += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(raw[c]));
-          mx1 = fmaxf(mx1, __uint_as_float(raw[c + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(raw[c + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(raw[c + 3]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-        // lazy rescaling: refresh the folded max only when it is stale by more than 2^8
-        float alpha = 1.f;
-        bool refresh = false;
-        if (mx > -INFINITY && (m_used == -INFINITY || (mx - m_used) * p.sl2 > RESCALE_THRESHOLD)) {
-          refresh = true;
-          alpha = (m_used == -INFINITY) ? 0.f : ex2((m_used - mx) * p.sl2);
-          m_used = mx;
-        }
-        if (j > 0 && __any_sync(0xffffffffu, refresh)) {
-          // O_x *= alpha (per row).  P_x(j-1) V(j-1) (and, in order, everything before it) must have landed first.
-          // Phase (j-1)/NSB of barrier (j-1)%NSB: its previous phase, P V (j-1-NSB), completed before S(j) was committed
-          // (Q K^T (j) is issued right after P V (j-NSB)).
-          mbar_wait(&o_done[x * NSB + (j - 1) % NSB], ((j - 1) / NSB) & 1);
-          tc_fence_after();
+        if (__any_sync(0xffffffffu, refresh)) {
 #pragma unroll 1
           for (int c = 0; c < 8; ++c) {               // rare path: small chunks keep the register footprint low
             uint32_t o[8];
@@ -306,35 +304,36 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           }
           tmem_wait_st();
         }
-        l_run *= alpha;
-        const float moff = (m_used == -INFINITY) ? 0.f : m_used * p.sl2;
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int t = 0; t < 16; t += 2) {
-            const float a0 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t]), p.sl2, -moff));
-            const float a1 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 1]), p.sl2, -moff));
-            const float a2 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 2]), p.sl2, -moff));
-            const float a3 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 3]), p.sl2, -moff));
-            r0 += a0; r1 += a1; r2 += a2; r3 += a3;
-            pk[t] = packp<BF16>(a0, a1);
-            pk[t + 1] = packp<BF16>(a2, a3);
-          }
-          tmem_st16(s_addr + buf * 64 + c * 16, pk);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&p_full[x * NSB + buf]);
-        l_run += (r0 + r1) + (r2 + r3);
       }
+      l_run *= alpha;
+      const float moff = (m_used == -INFINITY) ? 0.f : m_used * p.sl2;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 16; t += 2) {
+          const float a0 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t]), p.sl2, -moff));
+          const float a1 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 1]), p.sl2, -moff));
+          const float a2 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 2]), p.sl2, -moff));
+          const float a3 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 3]), p.sl2, -moff));
+          r0 += a0; r1 += a1; r2 += a2; r3 += a3;
+          pk[t] = packp<BF16>(a0, a1);
+          pk[t + 1] = packp<BF16>(a2, a3);
+        }
+        tmem_st16(p_addr + c * 16, pk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[x]);
+      l_run += (r0 + r1) + (r2 + r3);
+      ++j;
     }
 
     // ---- epilogue: wait for the last P V, normalise, store
     uint32_t accr[HD];
     if (j > 0) {
-      mbar_wait(&o_done[x * NSB + (j - 1) % NSB], ((j - 1) / NSB) & 1);      // last P V; MMAs complete in order
+      mbar_wait(&o_done[x], (j - 1) & 1);      // last P V (every earlier phase was waited for in the loop)
       tc_fence_after();
       tmem_ld32(o_addr, *reinterpret_cast<uint32_t(*)[32]>(&accr[0]));
       tmem_ld32(o_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&accr[32]));
