@@ -92,6 +92,43 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2): two lanes per issue slot on the FMA pipe
+__device__ __forceinline__ uint64_t pk2(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void up2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// 2^x for a pair on the FMA/ALU pipes instead of the MUFU: Cody-Waite split x = n + f (round to nearest via the
+// 1.5*2^23 magic add), degree-3 minimax polynomial for 2^f on [-0.5,0.5] (max rel. error 1.0e-4, below the 16-bit
+// rounding of P), n added straight into the exponent field.  At head_dim 64 the 16/clk/SM MUFU is the binding unit
+// of attention; moving 3 of every 8 pairs here balances MUFU time against issue slots.
+struct PolyC { uint64_t magic, c3, c2, c1, c0; };
+__device__ __forceinline__ PolyC make_polyc() {
+  PolyC c;
+  c.magic = pk2(12582912.f, 12582912.f);
+  c.c3 = pk2(0.0559220351f, 0.0559220351f);
+  c.c2 = pk2(0.242640078f, 0.242640078f);
+  c.c1 = pk2(0.693121016f, 0.693121016f);
+  c.c0 = pk2(0.999924481f, 0.999924481f);
+  return c;
+}
+__device__ __forceinline__ void ex2_poly2(uint64_t v, const PolyC& c, float& r0, float& r1) {
+  float x0, x1;
+  up2(v, x0, x1);
+  v = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));          // -inf (masked) -> 2^-125, which rounds to 0 in 16 bits
+  const uint64_t t = add2(v, c.magic);
+  const uint64_t f = sub2(v, sub2(t, c.magic));
+  uint64_t q = fma2(f, c.c3, c.c2);
+  q = fma2(q, f, c.c1);
+  q = fma2(q, f, c.c0);
+  float q0, q1, t0, t1;
+  up2(q, q0, q1);
+  up2(t, t0, t1);
+  r0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(t0) << 23));
+  r1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(t1) << 23));
+}
+
 template <bool BF16> __device__ __forceinline__ uint32_t packp(float lo, float hi) {
   uint32_t r;
   if (BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -99,7 +136,7 @@ template <bool BF16> __device__ __forceinline__ uint32_t packp(float lo, float h
   return r;
 }
 
-template <bool BF16, int QT>
+template <bool BF16, int QT, bool POLY>
 __global__ void __launch_bounds__(AttnCfg<QT>::THREADS, QT == 1 ? 2 : 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
             const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -245,6 +282,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     const uint32_t o_addr = s_addr + 192;
     float m_used = -INFINITY;      // max currently folded into the exponent (raw score units)
     float l_run = 0.f;
+    const PolyC polyc = make_polyc();
 
     TileWalk walk(p.Nk0, p.Nk1, lo, hi);
     TileIt it;
@@ -307,22 +345,31 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       }
       l_run *= alpha;
       const float moff = (m_used == -INFINITY) ? 0.f : m_used * p.sl2;
-      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+      const uint64_t sl2_2 = pk2(p.sl2, p.sl2), nmoff2 = pk2(-moff, -moff);
+      uint64_t rs0 = pk2(0.f, 0.f), rs1 = rs0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
-        for (int t = 0; t < 16; t += 2) {
-          const float a0 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t]), p.sl2, -moff));
-          const float a1 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 1]), p.sl2, -moff));
-          const float a2 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 2]), p.sl2, -moff));
-          const float a3 = ex2(fmaf(__uint_as_float(raw[c * 32 + 2 * t + 3]), p.sl2, -moff));
-          r0 += a0; r1 += a1; r2 += a2; r3 += a3;
+        for (int t = 0; t < 16; ++t) {
+          const uint64_t v = fma2(pk2(__uint_as_float(raw[c * 32 + 2 * t]), __uint_as_float(raw[c * 32 + 2 * t + 1])), sl2_2, nmoff2);
+          float a0, a1;
+          if (POLY && (t & 7) >= 5) {              // 3 of every 8 pairs on the FMA / ALU pipes
+            ex2_poly2(v, polyc, a0, a1);
+          } else {
+            float x0, x1;
+            up2(v, x0, x1);
+            a0 = ex2(x0);
+            a1 = ex2(x1);
+          }
+          if (t & 1) rs1 = add2(rs1, pk2(a0, a1)); else rs0 = add2(rs0, pk2(a0, a1));
           pk[t] = packp<BF16>(a0, a1);
-          pk[t + 1] = packp<BF16>(a2, a3);
         }
         tmem_st16(p_addr + c * 16, pk);
       }
+      float r0, r1, r2, r3;
+      up2(rs0, r0, r1);
+      up2(rs1, r2, r3);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[x]);
@@ -413,18 +460,18 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restri
   }
 }
 
-template <bool BF16, int QT>
+template <bool BF16, int QT, bool POLY>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                        const CUtensorMap& tmV1, const AttnParams& p, int B, cudaStream_t s) {
   using Cfg = AttnCfg<QT>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<BF16, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<BF16, QT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((p.Nq + QT * AT_BM - 1) / (QT * AT_BM), p.H, B * p.splits);
-  cudaError_t e = launch_pdl(attn_kernel<BF16, QT>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  cudaError_t e = launch_pdl(attn_kernel<BF16, QT, POLY>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, tmQ, tmK0, tmV0, tmK1, tmV1, p);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -510,9 +557,14 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     const double nk_eff = (double)(a->Nk0 + a->Nk1 - a->skip_len);
     ProfScope prof(qt == 2 ? PROF_ATTN_QT2 : PROF_ATTN_QT1, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
                    2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)Bkv * (a->Nk0 + a->Nk1) * a->H * HD * 2), cs);
+    static int poly = -1;
+    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = (e && e[0] == '0') ? 0 : 1; }
     int rc;
-    if (a->is_bf16) rc = qt == 2 ? launch_attn<true, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) : launch_attn<true, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs);
-    else rc = qt == 2 ? launch_attn<false, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) : launch_attn<false, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs);
+#define M3R_LAUNCH_ATTN(BF, QTV) (poly ? launch_attn<BF, QTV, true>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
+                                      : launch_attn<BF, QTV, false>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs))
+    if (a->is_bf16) rc = qt == 2 ? M3R_LAUNCH_ATTN(true, 2) : M3R_LAUNCH_ATTN(true, 1);
+    else rc = qt == 2 ? M3R_LAUNCH_ATTN(false, 2) : M3R_LAUNCH_ATTN(false, 1);
+#undef M3R_LAUNCH_ATTN
     if (rc) return rc;
     if (splits > 1) {
       const long long total = p.rows_total * a->H * 8;
