@@ -102,7 +102,8 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; a
 // 2^x for a pair on the FMA/ALU pipes instead of the MUFU: Cody-Waite split x = n + f (round to nearest via the
 // 1.5*2^23 magic add), degree-3 minimax polynomial for 2^f on [-0.5,0.5] (max rel. error 1.0e-4, below the 16-bit
 // rounding of P), n added straight into the exponent field.  At head_dim 64 the 16/clk/SM MUFU is the binding unit
-// of attention; moving 3 of every 8 pairs here balances MUFU time against issue slots.
+// of attention in theory; measured, the softmax warps are issue-slot-bound, so this path is OFF by
+// default (M3R_ATTN_POLY=1 enables it: 3 of every 8 pairs).
 struct PolyC { uint64_t magic, c3, c2, c1, c0; };
 __device__ __forceinline__ PolyC make_polyc() {
   PolyC c;
@@ -558,7 +559,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     ProfScope prof(qt == 2 ? PROF_ATTN_QT2 : PROF_ATTN_QT1, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
                    2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)Bkv * (a->Nk0 + a->Nk1) * a->H * HD * 2), cs);
     static int poly = -1;
-    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = (e && e[0] == '0') ? 0 : 1; }
+    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = (e && e[0] == '1') ? 1 : 0;   // measured on B200 (profiles/r01_attention_variants.txt): the kernel is issue-bound, the offload costs more slots than the MUFU time it frees }
     int rc;
 #define M3R_LAUNCH_ATTN(BF, QTV) (poly ? launch_attn<BF, QTV, true>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
                                       : launch_attn<BF, QTV, false>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs))
