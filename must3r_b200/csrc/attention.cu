@@ -559,7 +559,9 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     ProfScope prof(qt == 2 ? PROF_ATTN_QT2 : PROF_ATTN_QT1, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
                    2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)Bkv * (a->Nk0 + a->Nk1) * a->H * HD * 2), cs);
     static int poly = -1;
-    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = (e && e[0] == '1') ? 1 : 0;   // measured on B200 (profiles/r01_attention_variants.txt): the kernel is issue-bound, the offload costs more slots than the MUFU time it frees }
+    // measured on B200 (profiles/r01_attention_variants.txt): the kernel is issue-bound, so the polynomial offload costs
+    // more issue slots than the MUFU time it frees -> off unless M3R_ATTN_POLY=1
+    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = (e && e[0] == '1') ? 1 : 0; }
     int rc;
 #define M3R_LAUNCH_ATTN(BF, QTV) (poly ? launch_attn<BF, QTV, true>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
                                       : launch_attn<BF, QTV, false>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs))
