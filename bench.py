@@ -254,10 +254,11 @@ def main():
     # ---- profiled pass: per-category kernel time (CUDA events around every launch on the launch stream)
     roof, shares = None, None
     if rank == 0:
-        import ctypes as C
         lib.m3r_prof_enable(1)
-        job(imgs_dev, ts_dev)
-        torch.cuda.synchronize()
+    job(imgs_dev, ts_dev)          # every rank runs it (the sharded job contains collectives); only rank 0 records
+    torch.cuda.synchronize()
+    if rank == 0:
+        import ctypes as C
         buf = (C.c_double * 28)()
         lib.m3r_prof_read(buf)
         lib.m3r_prof_enable(0)
