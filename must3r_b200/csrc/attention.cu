@@ -52,6 +52,7 @@ struct AttnParams {
   long long ldo;
   float* part_o;             // [splits, B*Nq, H*64] fp32 unnormalised  (splits > 1)
   float* part_ml;            // [splits, B*Nq, H, 2]  (m_used * sl2, l)
+  int* split_cnt;            // [B, H, ceil(Nq/128)] arrival counters (zero on entry, reset by the last arriver)
   int H;
   long long rows_total;      // B * Nq
 };
@@ -137,7 +138,7 @@ template <bool BF16> __device__ __forceinline__ uint32_t packp(float lo, float h
   return r;
 }
 
-template <bool BF16, int QT, bool POLY>
+template <bool BF16, int QT, int POLY>
 __global__ void __launch_bounds__(AttnCfg<QT>::THREADS, QT == 1 ? 2 : 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
             const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -355,7 +356,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         for (int t = 0; t < 16; ++t) {
           const uint64_t v = fma2(pk2(__uint_as_float(raw[c * 32 + 2 * t]), __uint_as_float(raw[c * 32 + 2 * t + 1])), sl2_2, nmoff2);
           float a0, a1;
-          if (POLY && (t & 7) >= 5) {              // 3 of every 8 pairs on the FMA / ALU pipes
+          if (POLY > 0 && (t & 7) >= 8 - POLY) {   // POLY of every 8 pairs on the FMA / ALU pipes
             ex2_poly2(v, polyc, a0, a1);
           } else {
             float x0, x1;
@@ -415,6 +416,54 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         *ml = make_float2(m_used == -INFINITY ? -INFINITY : m_used * p.sl2, l_run);
       }
     }
+    if (p.splits > 1) {
+      // ---- merge of the key-range splits by the last CTA to finish this (batch, head, query tile):
+      // out = sum_s O_s 2^(m_s - m) / sum_s l_s 2^(m_s - m).  No extra kernel launch on the one-view-per-step chain.
+      __shared__ int s_last[2];
+      __threadfence();                                              // partials visible device-wide
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");    // the 4 warps of this warpgroup
+      const int n_qtiles = (p.Nq + AT_BM - 1) / AT_BM;
+      int* cnt = p.split_cnt + ((long long)b * p.H + h) * n_qtiles + (q0 / AT_BM + x);
+      if (row == 0) {
+        const int prev = atomicAdd(cnt, 1);
+        s_last[x] = (prev == p.splits - 1);
+        if (prev == p.splits - 1) *cnt = 0;                         // self-cleaning for the next launch
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+      if (s_last[x] && q_idx < p.Nq) {
+        __threadfence();
+        const long long grow = (long long)b * p.Nq + q_idx;
+        float m = -INFINITY;
+        for (int sp = 0; sp < p.splits; ++sp)
+          m = fmaxf(m, __ldcg(p.part_ml + (((long long)sp * p.rows_total + grow) * p.H + h) * 2));
+        float l = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+        for (int sp = 0; sp < p.splits; ++sp) {
+          const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml) + ((long long)sp * p.rows_total + grow) * p.H + h);
+          const float wgt = (ml.x == -INFINITY) ? 0.f : ex2(ml.x - m);
+          l += ml.y * wgt;
+          const float4* o = reinterpret_cast<const float4*>(p.part_o + ((long long)sp * p.rows_total + grow) * (p.H * HD) + h * HD);
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const float4 v = __ldcg(o + t);
+            acc[4 * t] = fmaf(v.x, wgt, acc[4 * t]); acc[4 * t + 1] = fmaf(v.y, wgt, acc[4 * t + 1]);
+            acc[4 * t + 2] = fmaf(v.z, wgt, acc[4 * t + 2]); acc[4 * t + 3] = fmaf(v.w, wgt, acc[4 * t + 3]);
+          }
+        }
+        const float inv = l > 0.f ? 1.0f / l : 0.f;
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          uint4 w;
+          w.x = packp<BF16>(acc[8 * t] * inv, acc[8 * t + 1] * inv);
+          w.y = packp<BF16>(acc[8 * t + 2] * inv, acc[8 * t + 3] * inv);
+          w.z = packp<BF16>(acc[8 * t + 4] * inv, acc[8 * t + 5] * inv);
+          w.w = packp<BF16>(acc[8 * t + 6] * inv, acc[8 * t + 7] * inv);
+          o4[t] = w;
+        }
+      }
+    }
   }
 
   tc_fence_before();
@@ -461,7 +510,7 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const float* __restri
   }
 }
 
-template <bool BF16, int QT, bool POLY>
+template <bool BF16, int QT, int POLY>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                        const CUtensorMap& tmV1, const AttnParams& p, int B, cudaStream_t s) {
   using Cfg = AttnCfg<QT>;
@@ -542,43 +591,43 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   p.skip_lo = a->skip_lo; p.skip_step = a->skip_step; p.skip_len = a->skip_len;
   p.splits = splits; p.sl2 = a->scale * 1.4426950408889634f;
   p.O = a->O; p.ldo = a->ldo; p.H = a->H; p.rows_total = (long long)a->B * a->Nq;
-  p.part_o = nullptr; p.part_ml = nullptr;
+  p.part_o = nullptr; p.part_ml = nullptr; p.split_cnt = nullptr;
   if (splits > 1) {
-    const size_t need = (size_t)splits * p.rows_total * a->H * (HD + 2);
+    // scratch layout: [4096 arrival counters | partial O | partial (m, l)].  The counters sit at a fixed place, are
+    // zeroed once when the buffer is (re)allocated and every launch leaves them zero again (last arriver resets).
+    constexpr size_t CNT = 4096;
+    const size_t n_cnt = (size_t)a->B * a->H * ((a->Nq + AT_BM - 1) / AT_BM);
+    if (n_cnt > CNT) return set_error("attention: too many (batch, head, tile) groups for the split path");
+    const size_t need = CNT + (size_t)splits * p.rows_total * a->H * (HD + 2);
     if (need > g_split_cap) {
       if (g_split_buf) cudaFreeAsync(g_split_buf, cs);
       g_split_buf = nullptr; g_split_cap = 0;
-      if (cudaMallocAsync(&g_split_buf, need * sizeof(float), cs) != cudaSuccess) return set_error("attention: split scratch allocation failed");
-      g_split_cap = need;
+      const size_t cap = need + need / 2;
+      if (cudaMallocAsync(&g_split_buf, cap * sizeof(float), cs) != cudaSuccess) return set_error("attention: split scratch allocation failed");
+      if (cudaMemsetAsync(g_split_buf, 0, CNT * sizeof(int), cs) != cudaSuccess) return set_error("attention: counter memset failed");
+      g_split_cap = cap;
     }
-    p.part_o = g_split_buf;
-    p.part_ml = g_split_buf + (size_t)splits * p.rows_total * a->H * HD;
+    p.split_cnt = reinterpret_cast<int*>(g_split_buf);
+    p.part_o = g_split_buf + CNT;
+    p.part_ml = p.part_o + (size_t)splits * p.rows_total * a->H * HD;
   }
   {
     const double nk_eff = (double)(a->Nk0 + a->Nk1 - a->skip_len);
     ProfScope prof(qt == 2 ? PROF_ATTN_QT2 : PROF_ATTN_QT1, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
                    2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)Bkv * (a->Nk0 + a->Nk1) * a->H * HD * 2), cs);
+    // Number of exponential pairs (out of every 8) evaluated by the polynomial instead of the MUFU.  Measured on B200
+    // (profiles/r01_attention_variants.txt): 3/8 makes the issue-bound softmax slower, 0 is the shipped default.
     static int poly = -1;
-    // measured on B200 (profiles/r01_attention_variants.txt): the kernel is issue-bound, so the polynomial offload costs
-    // more issue slots than the MUFU time it frees -> off unless M3R_ATTN_POLY=1
-    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = (e && e[0] == '1') ? 1 : 0; }
+    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = e ? atoi(e) : 0; if (poly < 0 || poly > 3) poly = 0; }
     int rc;
-#define M3R_LAUNCH_ATTN(BF, QTV) (poly ? launch_attn<BF, QTV, true>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
-                                      : launch_attn<BF, QTV, false>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs))
+#define M3R_LAUNCH_ATTN(BF, QTV) (poly == 0 ? launch_attn<BF, QTV, 0>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
+                                  : poly == 1 ? launch_attn<BF, QTV, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
+                                  : poly == 2 ? launch_attn<BF, QTV, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
+                                              : launch_attn<BF, QTV, 3>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs))
     if (a->is_bf16) rc = qt == 2 ? M3R_LAUNCH_ATTN(true, 2) : M3R_LAUNCH_ATTN(true, 1);
     else rc = qt == 2 ? M3R_LAUNCH_ATTN(false, 2) : M3R_LAUNCH_ATTN(false, 1);
 #undef M3R_LAUNCH_ATTN
     if (rc) return rc;
-    if (splits > 1) {
-      const long long total = p.rows_total * a->H * 8;
-      const int grid = (int)((total + 255) / 256 < (long long)sms * 8 ? (total + 255) / 256 : (long long)sms * 8);
-      cudaError_t e;
-      if (a->is_bf16) e = launch_pdl(attn_combine_kernel<true>, dim3(grid), dim3(256), 0, cs, (const float*)p.part_o, (const float*)p.part_ml, splits, p.rows_total, a->H, reinterpret_cast<uint16_t*>(a->O), (long long)a->ldo);
-      else e = launch_pdl(attn_combine_kernel<false>, dim3(grid), dim3(256), 0, cs, (const float*)p.part_o, (const float*)p.part_ml, splits, p.rows_total, a->H, reinterpret_cast<uint16_t*>(a->O), (long long)a->ldo);
-      if (e == cudaSuccess) e = cudaGetLastError();
-      if (e != cudaSuccess) return set_error("attention combine launch: %s", cudaGetErrorString(e));
-      count_launch();
-    }
   }
   return 0;
 }

@@ -1,0 +1,15 @@
+#!/bin/bash
+mkdir -p gpurun_out
+LOG=gpurun_out/run11.log
+: > $LOG
+run() { echo "=== $*" >> $LOG; timeout ${TMO:-600} "$@" >> $LOG 2>&1; echo "--- exit $?" >> $LOG; }
+run python tools/debug_attn.py
+run python -m pytest tests -q -x -m gpu --no-header -p no:cacheprovider
+run python tools/prof_step.py
+run python tools/prof_attn.py attn
+M3R_ATTN_POLY=1 run python tools/prof_attn.py attn
+M3R_ATTN_POLY=2 run python tools/prof_attn.py attn
+run python bench.py --steps 5 --warmup 3 --no-cpu-baseline
+grep -E "^(===|--- exit|[0-9]+ (passed|failed)|FAILED|ERROR|attn |update step|render \()" $LOG | cut -c1-250
+grep -o '"value": [0-9.]*, "unit": "views/s", "n_gpus"' $LOG
+grep -o '"e2e": {[^}]*}' $LOG
