@@ -615,10 +615,11 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     const double nk_eff = (double)(a->Nk0 + a->Nk1 - a->skip_len);
     ProfScope prof(qt == 2 ? PROF_ATTN_QT2 : PROF_ATTN_QT1, 4.0 * a->B * (double)a->H * a->Nq * nk_eff * HD,
                    2.0 * ((double)a->B * a->Nq * a->H * HD * 2 + (double)Bkv * (a->Nk0 + a->Nk1) * a->H * HD * 2), cs);
-    // Number of exponential pairs (out of every 8) evaluated by the polynomial instead of the MUFU.  Measured on B200
-    // (profiles/r01_attention_variants.txt): 3/8 makes the issue-bound softmax slower, 0 is the shipped default.
+    // Number of exponential pairs (out of every 8) evaluated by the polynomial instead of the MUFU.  Measured on B200 in
+    // one run (profiles/r01_attention_variants.txt): 0 -> 988 us, 1 -> 917 us, 2 -> 1082 us, 3 -> slower still
+    // (the softmax warps become issue-bound); 1 of 8 is the shipped default.
     static int poly = -1;
-    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = e ? atoi(e) : 0; if (poly < 0 || poly > 3) poly = 0; }
+    if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = e ? atoi(e) : 1; if (poly < 0 || poly > 3) poly = 1; }
     int rc;
 #define M3R_LAUNCH_ATTN(BF, QTV) (poly == 0 ? launch_attn<BF, QTV, 0>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
                                   : poly == 1 ? launch_attn<BF, QTV, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
