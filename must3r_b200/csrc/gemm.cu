@@ -2,7 +2,7 @@
 //
 //   warp 0      : TMA producer (one elected lane) -- A and W tiles, 128B-swizzled, mbarrier ring
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 per instruction)
-//   warps 2..5  : epilogue -- tcgen05.ld the fp32 accumulator (one row per thread), bias / RoPE / GELU /
+//   warps 2..9  : epilogue -- tcgen05.ld the fp32 accumulator (one row per thread, half the columns per warp), bias / RoPE / GELU /
 //                 residual / image2-embed row bias, vectorised global stores
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Tiles are walked m-fastest so that co-resident CTAs share the weight tile in L2.
@@ -14,7 +14,7 @@ namespace m3r {
 constexpr int BM = 128;
 constexpr int BK = 64;        // 64 x 16-bit = 128 B = one swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;      // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter, half the columns each)
 constexpr int SMEM_BUDGET = 196608;  // bytes of operand ring
 
 template <int BN>
@@ -140,7 +140,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -199,8 +199,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps (2..5)
+    // ------------------------------------------------------------ epilogue warps (2..9)
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;            // which half of the tile's columns this warp drains
     const int lane = threadIdx.x & 31;
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -217,11 +218,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         uint32_t raw[32];
         tmem_ld32(t_addr + c * 32, raw);
         tmem_wait_ld();
-        if (c == BN / 32 - 1) {                  // accumulator fully read: hand the buffer back early
+        if (c == (chalf + 1) * (BN / 64) - 1) {  // this warp's share of the accumulator is read: hand it back early
           tc_fence_before();
           mbar_arrive(&tempty[as]);
         }
@@ -292,7 +293,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* full = bars;                       // [P_STAGES] used in the leader only
   uint64_t* empty = bars + P_STAGES;           // [P_STAGES] both CTAs (multicast commit)
   uint64_t* tfull = bars + 2 * P_STAGES;       // [2] both CTAs (multicast commit)
-  uint64_t* tempty = bars + 2 * P_STAGES + 2;  // [2] leader only: 256 arrivals (both CTAs' epilogue threads)
+  uint64_t* tempty = bars + 2 * P_STAGES + 2;  // [2] leader only: 512 arrivals (both CTAs' epilogue threads)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * P_STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -308,7 +309,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 256); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 512); }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -369,6 +370,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
     const int quarter = warp & 3;
+    const int chalf = (warp - 2) >> 2;
     const int lane = threadIdx.x & 31;
     int as = 0; uint32_t aphase = 0;
     const uint32_t tempty_leader[2] = {mapa_u32(&tempty[0], 0), mapa_u32(&tempty[1], 0)};
@@ -385,11 +387,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + as * 256;
 #pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      for (int c = chalf * 4; c < chalf * 4 + 4; ++c) {
         uint32_t raw[32];
         tmem_ld32(t_addr + c * 32, raw);
         tmem_wait_ld();
-        if (c == 7) {
+        if (c == chalf * 4 + 3) {
           tc_fence_before();
           mbar_arrive_cluster(tempty_leader[as]);
         }
@@ -457,11 +459,13 @@ extern "C" int m3r_gemm(const m3r_gemm_args* a, void* stream) {
   if (a->N % 256 == 0 && tiles_m * (a->N / 256) >= sms) bn = 256;
   else if (a->N % 128 == 0 && tiles_m * (a->N / 128) >= sms) bn = 128;
   {
-    // CTA-pair kernel for problems with at least one 256x256 tile per SM pair (opt-in until measured: M3R_GEMM_PAIR=1)
+    // CTA-pair kernel for problems with at least one 256x256 tile per SM pair.  Measured (profiles/r01_run13_gemm_pair.log):
+    // +7..+20 % for K >= 1024, -1..-4 % for K = 768 (epilogue-bound tiles) -> used for K >= 1024; M3R_GEMM_PAIR=0/2
+    // force it off / on for every eligible shape.
     static int pair_mode = -1;
-    if (pair_mode < 0) { const char* e = getenv("M3R_GEMM_PAIR"); pair_mode = e ? atoi(e) : 0; }
-    if (pair_mode && a->N % 256 == 0 && ((a->M + 255) / 256) * (a->N / 256) >= sms / 2 && !getenv("M3R_GEMM_BN"))
-      return launch_gemm_pair(a, s);
+    if (pair_mode < 0) { const char* e = getenv("M3R_GEMM_PAIR"); pair_mode = e ? atoi(e) : 1; }
+    const bool eligible = a->N % 256 == 0 && ((a->M + 255) / 256) * (a->N / 256) >= sms / 2 && !getenv("M3R_GEMM_BN");
+    if (eligible && (pair_mode == 2 || (pair_mode == 1 && a->K >= 1024))) return launch_gemm_pair(a, s);
   }
   const char* force = getenv("M3R_GEMM_BN");
   if (force) { int f = atoi(force); if ((f == 64 || f == 128 || f == 256) && a->N % f == 0) bn = f; }

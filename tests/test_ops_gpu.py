@@ -52,6 +52,22 @@ def test_gemm_large_persistent(dtype):
     assert (out[sl].double() - ref64).abs().max() < 1e-4
 
 
+def test_gemm_cta_pair_kernel_forced():
+    """The cta_group::2 kernel forced on for every eligible shape (own process: the mode is latched at first use)."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, M3R_GEMM_PAIR="2")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "test_gemm_pair.py")], env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if "rel" in l]
+    assert len(lines) == 8
+    for l in lines:
+        vals = [float(t) for t in l.replace("rel", " ").split() if "e-" in t]
+        tol16 = 5e-3 if "bfloat16" in l else 6e-4
+        assert vals[0] < 2e-5 and vals[1] < tol16 and vals[2] < 2e-5, l
+
+
 @pytest.mark.parametrize("dtype", DT)
 def test_gemm_epilogues(dtype):
     M, N, K = 392, 768, 768
