@@ -19,7 +19,8 @@
 extern "C" {
 #endif
 
-#define M3R_ABI_VERSION 1
+#define M3R_ABI_VERSION 2
+#define M3R_MAX_PEERS 8
 
 /* out_dtype */
 #define M3R_OUT_F32 0
@@ -70,6 +71,11 @@ typedef struct {
   int32_t rows_per_batch; /* output row remap for appending into [B,cap,N] buffers:              */
   int64_t batch_stride_rows; /* out_row = (row / rows_per_batch) * batch_stride_rows + row % rows_per_batch;
                                 rows_per_batch <= 0 disables the remap */
+  /* Fused "GEMM -> all-gather": when n_peer_out > 0 the 16-bit output tile is ALSO stored, with the same row mapping
+   * and ldc, to these device pointers - the same buffer in the other GPUs of the NVSwitch domain, mapped into this
+   * process with m3r_ipc_open (peer stores travel over NVLink while the kernel is still computing other tiles). */
+  int32_t n_peer_out;
+  void* peer_out[M3R_MAX_PEERS];
 } m3r_gemm_args;
 
 int m3r_gemm(const m3r_gemm_args* args, void* stream);
@@ -229,9 +235,23 @@ typedef struct {
   int32_t new_only;                /* update only: 1 = mem_out[l] is [B, Nt, 2D] and receives ONLY the new post-feedback
                                       K|V rows (no copy of the old memory) - used by the sharded schedule, where the new
                                       tokens of all ranks are all-gathered into a pre-allocated memory buffer */
+  int32_t n_peers;                 /* > 0 (with new_only): the post-feedback K|V GEMM epilogue stores the new rows straight
+                                      into every rank's memory buffer (fused GEMM -> all-gather over NVLink peer memory) */
+  void* const* peer_mem;           /* host array [n_peers * depth]: peer_mem[r * depth + l] = rank r's memory buffer of
+                                      level l ([1, cap, 2D] 16-bit), already offset to the row where THIS rank's tokens go */
 } m3r_decoder_call;
 
 int64_t m3r_decoder_workspace_bytes(const m3r_decoder_weights* w, const m3r_decoder_call* call);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Peer memory for the multi-GPU schedule (one process per GPU): buffers allocated with m3r_peer_alloc can be exported
+ * as a 64-byte CUDA IPC handle, exchanged through torch.distributed, and mapped by the other ranks of the node.
+ * ------------------------------------------------------------------------------------------------- */
+int m3r_peer_alloc(int64_t bytes, void** ptr);
+int m3r_peer_free(void* ptr);
+int m3r_ipc_export(void* ptr, void* handle64);
+int m3r_ipc_open(const void* handle64, void** ptr);
+int m3r_ipc_close(void* ptr);
 
 /* MUSt3R.forward / forward_list (decoder.py:158-350) for memory_mode 'kv'. */
 int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decoder_call* call, void* workspace,

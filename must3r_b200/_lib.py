@@ -27,6 +27,8 @@ class GemmArgs(C.Structure):
         ("out_dtype", C.c_int32),
         ("rows_per_batch", C.c_int32),
         ("batch_stride_rows", C.c_int64),
+        ("n_peer_out", C.c_int32),
+        ("peer_out", C.c_void_p * 8),
     ]
 
 
@@ -62,6 +64,11 @@ SIGNATURES = {
     "m3r_im2col16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "m3r_unpatchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "m3r_postprocess": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "m3r_peer_alloc": (C.c_int, [C.c_int64, C.POINTER(C.c_void_p)]),
+    "m3r_peer_free": (C.c_int, [C.c_void_p]),
+    "m3r_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "m3r_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "m3r_ipc_close": (C.c_int, [C.c_void_p]),
 }
 
 

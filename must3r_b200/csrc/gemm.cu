@@ -41,6 +41,8 @@ struct GemmParams {
   int out_dtype;
   int rows_per_batch;
   long long batch_stride_rows;
+  int n_peer_out;
+  void* peer_out[M3R_MAX_PEERS];
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -109,6 +111,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         w.z = pack16(v[8 * i + 4], v[8 * i + 5], p.is_bf16);
         w.w = pack16(v[8 * i + 6], v[8 * i + 7], p.is_bf16);
         o4[i] = w;
+        // fused all-gather: the same 16 bytes go to the other GPUs' copies of the buffer (NVLink peer stores)
+        for (int pr = 0; pr < p.n_peer_out; ++pr)
+          reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.peer_out[pr]) + orow * p.ldc + col0)[i] = w;
       }
     }
   }
@@ -253,6 +258,8 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream) {
   p.rope_tab = a->rope_tab; p.rope_cols = a->rope_cols; p.rope_period = a->rope_period > 0 ? a->rope_period : 1;
   p.out = a->out; p.ldc = a->ldc; p.out_dtype = a->out_dtype;
   p.rows_per_batch = a->rows_per_batch; p.batch_stride_rows = a->batch_stride_rows;
+  p.n_peer_out = a->n_peer_out;
+  for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -420,6 +427,8 @@ static int launch_gemm_pair(const m3r_gemm_args* a, cudaStream_t stream) {
   p.rope_tab = a->rope_tab; p.rope_cols = a->rope_cols; p.rope_period = a->rope_period > 0 ? a->rope_period : 1;
   p.out = a->out; p.ldc = a->ldc; p.out_dtype = a->out_dtype;
   p.rows_per_batch = a->rows_per_batch; p.batch_stride_rows = a->batch_stride_rows;
+  p.n_peer_out = a->n_peer_out;
+  for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
@@ -451,6 +460,7 @@ extern "C" int m3r_gemm(const m3r_gemm_args* a, void* stream) {
   if ((a->out_dtype == M3R_OUT_F32 && a->ldc % 4) || (a->out_dtype == M3R_OUT_16 && a->ldc % 8)) return set_error("gemm: ldc alignment");
   if (a->residual && a->ldr % 4) return set_error("gemm: ldr alignment");
   if (a->rope_tab && (a->rope_cols % 64)) return set_error("gemm: rope_cols must be a multiple of 64");
+  if (a->n_peer_out < 0 || a->n_peer_out > M3R_MAX_PEERS || (a->n_peer_out > 0 && a->out_dtype != M3R_OUT_16)) return set_error("gemm: peer outputs need 0..%d pointers and a 16-bit output", M3R_MAX_PEERS);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   // Tile-width heuristic: widest BN that still yields about one wave of CTAs.
   const int tiles_m = (a->M + BM - 1) / BM;

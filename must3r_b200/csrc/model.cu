@@ -32,8 +32,10 @@ static int gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, i
                 const float* bias, int act, const float* residual, int64_t ldr, void* out, int64_t ldc, int out_dtype,
                 void* stream, const float* rope_tab = nullptr, int rope_cols = 0, int rope_period = 0,
                 const float* rowbias = nullptr, int rb_period = 1, int rb_first = 0, int rows_per_batch = 0,
-                int64_t batch_stride_rows = 0) {
+                int64_t batch_stride_rows = 0, int n_peer_out = 0, void* const* peer_out = nullptr) {
   m3r_gemm_args a;
+  a.n_peer_out = n_peer_out;
+  for (int i = 0; i < M3R_MAX_PEERS; ++i) a.peer_out[i] = i < n_peer_out ? peer_out[i] : nullptr;
   a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.M = M; a.N = N; a.K = K; a.is_bf16 = is_bf16;
   a.bias = bias; a.act = act; a.residual = residual; a.ldr = ldr;
   a.rowbias = rowbias; a.rb_period = rb_period; a.rb_first = rb_first;
@@ -189,6 +191,8 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   if (c->render && c->Nm <= 0) return set_error("decoder_forward: render needs a memory (decoder.py:278)");
   if (c->Nm > 0 && !c->mem) return set_error("decoder_forward: memory pointers missing");
   if (!c->render && !c->mem_out) return set_error("decoder_forward: mem_out missing");
+  if (c->n_peers < 0 || c->n_peers > M3R_MAX_PEERS || (c->n_peers > 0 && (!c->peer_mem || !c->new_only || c->B != 1)))
+    return set_error("decoder_forward: peer output needs new_only, one scene and 1..%d peers", M3R_MAX_PEERS);
   DecWs ws;
   const int64_t need = dec_layout(w, c, workspace, workspace_bytes, &ws);
   if (need > workspace_bytes) return set_error("decoder_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
@@ -328,9 +332,12 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
       for (int g = 0; g < G; ++g) {
         const m3r_dec_group& gr = c->groups[g];
         const int Mg = B * gr.n_views * gr.N;
+        void* peers[M3R_MAX_PEERS];
+        for (int r = 0; r < c->n_peers; ++r)
+          peers[r] = reinterpret_cast<uint16_t*>(c->peer_mem[r * w->depth + l]) + ws.tok0[g] * 2 * D;
         M3R_TRY(gemm(hbuf + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
                      mo + ((int64_t)(c->new_only ? 0 : Nm) + ws.tok0[g]) * 2 * D, 2 * D, M3R_OUT_16, st, nullptr, 0, 0, nullptr, 1, 0,
-                     gr.n_views * gr.N, c->mem_out_bstride_rows));
+                     gr.n_views * gr.N, c->mem_out_bstride_rows, c->n_peers, peers));
       }
     }
     return 0;

@@ -134,3 +134,29 @@ extern "C" int m3r_prof_read(double* out) {
   }
   return 0;
 }
+
+extern "C" int m3r_peer_alloc(int64_t bytes, void** ptr) {
+  if (!ptr || bytes <= 0) return m3r::set_error("peer_alloc: bad arguments");
+  cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+  if (e != cudaSuccess) return m3r::set_error("peer_alloc: cudaMalloc(%lld) failed: %s", (long long)bytes, cudaGetErrorString(e));
+  return 0;
+}
+extern "C" int m3r_peer_free(void* ptr) {
+  cudaError_t e = cudaFree(ptr);
+  return e == cudaSuccess ? 0 : m3r::set_error("peer_free: %s", cudaGetErrorString(e));
+}
+extern "C" int m3r_ipc_export(void* ptr, void* handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaError_t e = cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t*>(handle64), ptr);
+  return e == cudaSuccess ? 0 : m3r::set_error("ipc_export: %s", cudaGetErrorString(e));
+}
+extern "C" int m3r_ipc_open(const void* handle64, void** ptr) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+  return e == cudaSuccess ? 0 : m3r::set_error("ipc_open: %s", cudaGetErrorString(e));
+}
+extern "C" int m3r_ipc_close(void* ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  return e == cudaSuccess ? 0 : m3r::set_error("ipc_close: %s", cudaGetErrorString(e));
+}

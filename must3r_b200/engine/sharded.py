@@ -13,6 +13,11 @@ number V of views of ONE scene (global view id = rank * V + i):
      labels in rank order;
   4. render: each rank renders its V views against the final replicated memory (no collective).
 
+On CUDA with the must3r_b200 decoder the gather is FUSED into the producing GEMM: the memory buffers live in
+peer-visible device memory (`engine/peer.py`, CUDA IPC) and the epilogue of the post-feedback K|V projection stores each
+16-bit tile into every rank's buffer over NVLink while the kernel is still computing other tiles; a barrier per round
+replaces the all-gather (M3R_FUSED_GATHER=0 selects the NCCL all-gather path, which is also what gloo/CPU runs use).
+
 With world_size 1 the schedule degenerates to the reference chain (init 2 views, then 1 view per step).
 The oracle for world_size > 1 is composed from single-process decoder calls only (tests/test_sharded_cpu.py).
 The function is model-agnostic: decoders exposing ``update_tokens`` (the CUDA MUSt3R) avoid materialising the
@@ -20,10 +25,14 @@ concatenated memory; any reference-style decoder works through ``mem'[0][l][:, N
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional
 
 import torch
 import torch.distributed as dist
+
+_LIVE_ARENAS = []      # arenas backing memory tuples handed back to callers (return_mem=True)
+_ARENA_CACHE = {}      # (nbytes, device) -> PeerArena reused by calls that do not hand their memory back
 
 
 def _world():
@@ -94,41 +103,82 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
         labels[0, Nm:Nm + cnt] = lab.repeat_interleave(N)
         n_mem_views += len(sel) * n_each
 
-    # ---- 2. init on rank 0 (views 0,1); every rank runs the same gather so the memory is replicated
     n_init = min(2, V)
-    if rank == 0:
-        toks, _ = _new_tokens(decoder, x[None, :n_init], pos[None, :n_init], true_shape[None, :n_init], None)
-        packed = torch.stack([t[0] for t in toks], 0)                                  # [depth, n_init*N, mem_D]
-    else:
-        packed = None
-    if world > 1:
-        shape = [0, 0, 0]
-        if rank == 0:
-            shape = list(packed.shape)
-        st = torch.tensor(shape, dtype=torch.int64, device=device)
-        dist.broadcast(st, src=0)
-        if rank != 0:
-            dt = getattr(decoder, "memory_dtype", None)
-            dt = dt() if callable(dt) else (dt or torch.float32)
-            packed = torch.empty(tuple(int(v) for v in st.tolist()), dtype=dt, device=device)
-        dist.broadcast(packed, src=0)
-    append(packed[None] if world == 1 else packed[None].expand(world, *packed.shape),
-           [r == 0 for r in range(world)], n_init)
+    fused = (world > 1 and x.is_cuda and hasattr(decoder, "update_tokens_to_peers")
+             and os.environ.get("M3R_FUSED_GATHER", "1") != "0")
+    arena = None
+    if fused:
+        # ---- fused GEMM -> all-gather: every rank's memory buffers are peer-mapped; producers store into all of them
+        from .peer import PeerArena
+        depth, mem_D, dt = decoder.depth, 2 * decoder.embed_dim, decoder.memory_dtype()
+        cap = world * V * N
+        esz = torch.empty((), dtype=dt).element_size()
+        akey = (depth * cap * mem_D * esz, str(x.device))
+        arena = None if return_mem else _ARENA_CACHE.get(akey)
+        if arena is None:
+            arena = PeerArena(akey[0], x.device)          # collective: every rank allocates, exports and maps
+            if not return_mem:
+                _ARENA_CACHE[akey] = arena
+        mem_vals = [arena.local[l * cap * mem_D * esz:(l + 1) * cap * mem_D * esz].view(dt).view(1, cap, mem_D) for l in range(depth)]
+        labels = torch.empty((1, cap), dtype=torch.int64, device=x.device)
 
-    # ---- 3. update rounds: one view per rank per round, one all-gather per round
-    for s in range(V):
-        mine = not (rank == 0 and s < n_init)
-        flags = [not (r == 0 and s < n_init) for r in range(world)]
-        if not any(flags):
-            continue
-        # ranks that sit a round out still take part in the collective (with a dummy payload)
-        if mine:
-            toks, _ = _new_tokens(decoder, x[None, s:s + 1], pos[None, s:s + 1], true_shape[None, s:s + 1], current_mem())
-            packed = torch.stack([t[0] for t in toks], 0)                              # [depth, N, mem_D]
+        def dests(row):       # peer_ptrs[r][l] for new tokens starting at memory row `row`
+            return [[arena.ptrs[r] + (l * cap + row) * mem_D * esz for l in range(depth)] for r in range(world)]
+
+        def commit(n_views_added):
+            nonlocal n_mem_views
+            Nm = n_mem_views * N
+            cnt = n_views_added * N
+            labels[0, Nm:Nm + cnt] = torch.arange(n_mem_views, n_mem_views + n_views_added, device=labels.device).repeat_interleave(N)
+            n_mem_views += n_views_added
+            dist.barrier()        # every rank's peer stores have landed before anyone reads the new rows
+
+        if rank == 0:
+            decoder.update_tokens_to_peers(x[None, :n_init], pos[None, :n_init], true_shape[None, :n_init], None, dests(0))
+        commit(n_init)
+        for s in range(V):
+            flags = [not (r == 0 and s < n_init) for r in range(world)]
+            if flags[rank]:
+                slot = sum(flags[:rank])
+                decoder.update_tokens_to_peers(x[None, s:s + 1], pos[None, s:s + 1], true_shape[None, s:s + 1], current_mem(),
+                                               dests((n_mem_views + slot) * N))
+            commit(sum(flags))
+
+    # ---- 2. init on rank 0 (views 0,1); every rank runs the same gather so the memory is replicated
+    if not fused:
+        if rank == 0:
+            toks, _ = _new_tokens(decoder, x[None, :n_init], pos[None, :n_init], true_shape[None, :n_init], None)
+            packed = torch.stack([t[0] for t in toks], 0)                                  # [depth, n_init*N, mem_D]
         else:
-            packed = torch.zeros((len(mem_vals), N, mem_vals[0].shape[2]), dtype=mem_vals[0].dtype, device=device)
-        gathered = _all_gather(packed, world) if world > 1 else packed[None]
-        append(gathered, flags, 1)
+            packed = None
+        if world > 1:
+            shape = [0, 0, 0]
+            if rank == 0:
+                shape = list(packed.shape)
+            st = torch.tensor(shape, dtype=torch.int64, device=device)
+            dist.broadcast(st, src=0)
+            if rank != 0:
+                dt = getattr(decoder, "memory_dtype", None)
+                dt = dt() if callable(dt) else (dt or torch.float32)
+                packed = torch.empty(tuple(int(v) for v in st.tolist()), dtype=dt, device=device)
+            dist.broadcast(packed, src=0)
+        append(packed[None] if world == 1 else packed[None].expand(world, *packed.shape),
+               [r == 0 for r in range(world)], n_init)
+
+        # ---- 3. update rounds: one view per rank per round, one all-gather per round
+        for s in range(V):
+            mine = not (rank == 0 and s < n_init)
+            flags = [not (r == 0 and s < n_init) for r in range(world)]
+            if not any(flags):
+                continue
+            # ranks that sit a round out still take part in the collective (with a dummy payload)
+            if mine:
+                toks, _ = _new_tokens(decoder, x[None, s:s + 1], pos[None, s:s + 1], true_shape[None, s:s + 1], current_mem())
+                packed = torch.stack([t[0] for t in toks], 0)                              # [depth, N, mem_D]
+            else:
+                packed = torch.zeros((len(mem_vals), N, mem_vals[0].shape[2]), dtype=mem_vals[0].dtype, device=device)
+            gathered = _all_gather(packed, world) if world > 1 else packed[None]
+            append(gathered, flags, 1)
 
     # ---- 4. render this rank's views against the replicated memory
     mem = current_mem()
@@ -144,4 +194,6 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
         else:
             pm = pm.cpu() if to_host else pm
             outs.extend(pm[j] for j in range(pm.shape[0]))
+    if arena is not None and return_mem:
+        _LIVE_ARENAS.append(arena)           # the returned memory tensors are views of the arena
     return (mem, outs) if return_mem else outs

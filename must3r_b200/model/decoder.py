@@ -187,7 +187,17 @@ class MUSt3R(nn.Module):
         return new_tokens, pms[0]
 
     @torch.no_grad()
-    def forward_list(self, x, pos, true_shape, current_mem=None, render=False, return_feats=False, _new_only=False):
+    def update_tokens_to_peers(self, x, pos, true_shape, current_mem, peer_ptrs):
+        """Same update, but the post-feedback K|V GEMM epilogue also stores the new rows straight into every rank's memory
+        buffer: ``peer_ptrs[r][l]`` = device pointer (int) of rank r's level-l buffer at the row where this rank's tokens
+        belong (fused GEMM -> all-gather over NVLink peer memory; the caller synchronises the ranks afterwards)."""
+        _, pms, new_tokens = self.forward_list([x], [pos], [true_shape], current_mem, render=False, _new_only=True,
+                                               _peer_ptrs=peer_ptrs)
+        return new_tokens, pms[0]
+
+    @torch.no_grad()
+    def forward_list(self, x, pos, true_shape, current_mem=None, render=False, return_feats=False, _new_only=False,
+                     _peer_ptrs=None):
         """decoder.py:158-265"""
         if self.memory_mode != 'kv':
             raise NotImplementedError("must3r_b200 implements memory_mode='kv' (the released checkpoints' mode); "
@@ -259,6 +269,13 @@ class MUSt3R(nn.Module):
             call.mem_out = out_ptrs
             call.mem_out_bstride_rows = rows
             call.new_only = 1 if _new_only else 0
+            if _peer_ptrs:
+                flat = (C.c_void_p * (len(_peer_ptrs) * self.depth))()
+                for r, ptrs in enumerate(_peer_ptrs):
+                    for l in range(self.depth):
+                        flat[r * self.depth + l] = ptrs[l]
+                call.n_peers, call.peer_mem = len(_peer_ptrs), flat
+                keep.append(flat)
         nbytes = lib.m3r_decoder_workspace_bytes(C.byref(w), C.byref(call))
         ws = cm.workspace(dev, nbytes, "dec")
         _lib.check(lib.m3r_decoder_forward(C.byref(w), C.byref(call), C.c_void_p(ws.data_ptr()), ws.numel(), cm.stream_ptr()),
