@@ -52,6 +52,21 @@ def test_gemm_large_persistent(dtype):
     assert (out[sl].double() - ref64).abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("dtype", DT)
+def test_gemm_multi_destination_epilogue(dtype):
+    """Fused GEMM -> all-gather building block: the 16-bit tile is stored to every pointer of peer_out with the same
+    row mapping (here the 'peers' are other local buffers; over CUDA IPC they are the other GPUs' memory buffers)."""
+    M, N, K = 768, 1536, 768
+    a, w = rnd(M, K, dtype=dtype, seed=40), rnd(N, K, dtype=dtype, seed=41, scale=K ** -0.5)
+    bias = rnd(N, seed=42)
+    bufs = [torch.zeros(3 * M, N, device="cuda", dtype=dtype) for _ in range(3)]
+    out = ops.linear(a, w, bias, peer_ptrs=[b[M:].data_ptr() for b in bufs])
+    ref = a.float() @ w.float().t() + bias
+    assert rel_l2(out, ref) < OUT_TOL[dtype]
+    for b in bufs:
+        assert torch.equal(b[M:2 * M], out) and float(b[:M].abs().max()) == 0 and float(b[2 * M:].abs().max()) == 0
+
+
 def test_gemm_cta_pair_kernel_forced():
     """The cta_group::2 kernel forced on for every eligible shape (own process: the mode is latched at first use)."""
     import subprocess, sys
