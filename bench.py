@@ -190,7 +190,7 @@ def main():
     V = args.views
     imgs_host, ts_host = syn.synthetic_views(V, H, W, seed=2 + rank)
     imgs_pinned = imgs_host.pin_memory()
-    imgs_dev, ts_dev = imgs_host.to(dev), ts_host.to(dev)
+    imgs_dev, ts_dev = imgs_host.to(dev), ts_host       # true_shape: host tensor, like the reference's loaders produce
     pp = lambda pm: engine.postprocess(pm, ActivationType.NORM_EXP)  # noqa: E731
     lib = _lib.lib()
 
@@ -198,7 +198,7 @@ def main():
         """Public-API job: engine.encoder_multi_ar + engine.inference_multi_ar (or the sharded schedule at N>1)."""
         if world == 1:
             views = list(imgs.unbind(0))
-            tss = list(ts.unbind(0))
+            tss = list(ts.unbind(0))            # true_shape stays on the host (as it comes from an image loader)
             x, pos = engine.encoder_multi_ar(enc, views, ts, device=dev)
             ids = [torch.tensor(i) for i in range(V)]
             pm0, pm = engine.inference_multi_ar(enc, dec, views, ids, tss, [2] + [1] * (V - 2),

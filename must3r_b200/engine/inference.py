@@ -36,6 +36,21 @@ def _to_out(v, outdevice):
     return v.to(outdevice)
 
 
+def _with_host_shape(true_shape_group, device):
+    """true_shape [n,2] of one aspect-ratio group -> [1,n,2] on `device`.  When the caller's tensor lives on the host (the
+    usual case: it comes from the image loader) its (H, W) is attached as `_m3r_hw`, which lets the CUDA decoder skip the
+    device->host read the reference performs in every call (must3r/model/blocks/head.py:31-32)."""
+    out = true_shape_group.unsqueeze(0).to(device)
+    if not true_shape_group.is_cuda:
+        rows = true_shape_group.reshape(-1, 2)
+        assert bool((rows == rows[:1]).all()), 'true_shape must be all identical'
+        try:
+            out._m3r_hw = tuple(int(v) for v in rows[0].tolist())
+        except Exception:  # noqa: BLE001  (tensor subclasses that refuse attributes)
+            pass
+    return out
+
+
 def _sync_host_copies():
     if _PENDING_HOST_COPIES[0]:
         torch.cuda.current_stream().synchronize()
@@ -173,7 +188,7 @@ def inference_multi_ar_batch(encoder, decoder, imgs, true_shape, mem=None, verbo
         x, pos = encoder_precomputed_features
     x = [v.unsqueeze(0).to(device) for v in x]           # B = 1 scene
     pos = [v.unsqueeze(0).to(device) for v in pos]
-    ts = [v.unsqueeze(0).to(device) for v in true_shape]
+    ts = [_with_host_shape(v, device) for v in true_shape]
     mem, pms = decoder(x, pos, ts, mem, render=render)
     results = []
     for pm in pms:
@@ -208,7 +223,14 @@ def _update_in_mem(old_values, new_values, old_labels, new_labels, old_idx, new_
     return old_values
 
 
-def _fresh_labels(new_mem, n_before):
+def _fresh_labels(new_mem, n_before, mem_before=None, n_new_views=None):
+    """Labels given to the views of the last decoder call.  The reference reads them back from the label tensor
+    (`sorted(torch.unique(new_mem[1][:, Nmem_before:]))`, engine/inference.py:290,426 - a device sync per step); the decoder
+    assigns them deterministically as mem_nimgs + arange(n) (decoder.py:242-247,332-336), so they are computed on the host
+    when the call's view count is known."""
+    if n_new_views is not None:
+        first = 0 if mem_before is None else int(mem_before[2])
+        return list(range(first, first + n_new_views))
     return [int(v) for v in sorted(torch.unique(new_mem[1][:, n_before:]))]
 
 
@@ -258,6 +280,7 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
             x_i, pos_i = _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device)
             ts_st, idx_st, x_st, pos_st, img_st = stack_views(ts_i, [x_i, pos_i, imgs_i], max_bs=max_bs)
             n_before = get_Nmem(mem)
+            mem_prev = mem
             new_mem, res = inference_multi_ar_batch(encoder, decoder, img_st, ts_st, mem, verbose=verbose,
                                                     encoder_precomputed_features=(x_st, pos_st),
                                                     preserve_gpu_mem=preserve_gpu_mem,
@@ -266,7 +289,7 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
             res = unstack_pointmaps(idx_st, res)
             first_pass[lo:hi] = res
             mem = list(new_mem)
-            new_labels = _fresh_labels(mem, n_before)
+            new_labels = _fresh_labels(mem, n_before, mem_prev, hi - lo)
             if custom_callbacks:
                 _sync_host_copies()        # user callbacks may read the (host) results
             flags = []
@@ -340,7 +363,7 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
                                                         preserve_gpu_mem=preserve_gpu_mem,
                                                         post_process_function=post_process_function, device=device,
                                                         viser_server=viser_server)
-                new_labels = _fresh_labels(new_mem, get_Nmem(mem))
+                new_labels = _fresh_labels(new_mem, get_Nmem(mem), mem, hi - lo)
                 if refresh:
                     assert mem is not None
                     for j, vid in enumerate(ids_i):

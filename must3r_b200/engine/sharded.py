@@ -69,9 +69,24 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
     rank, world = _world()
     device = device or imgs.device
     V = imgs.shape[0]
-    imgs, true_shape = imgs.to(device), true_shape.to(device)
-    x, pos = encoder(imgs, true_shape)                         # [V,N,Denc], [V,N,2]
+    hw = None
+    if not true_shape.is_cuda:                                 # host copy of (H, W): spares a device sync per decoder call
+        assert bool((true_shape == true_shape[:1]).all()), "all views of a rank must share one true_shape"
+        hw = tuple(int(v) for v in true_shape[0].tolist())
+    imgs, ts_dev = imgs.to(device), true_shape.to(device)
+    x, pos = encoder(imgs, ts_dev)                             # [V,N,Denc], [V,N,2]
     N = x.shape[1]
+
+    class _TS:                                                 # true_shape[None, a:b] with the host hint attached
+        def __getitem__(self, idx):
+            t = ts_dev[idx]
+            if hw is not None:
+                try:
+                    t._m3r_hw = hw
+                except Exception:  # noqa: BLE001
+                    pass
+            return t
+    true_shape = _TS()
 
     mem_vals: Optional[List[torch.Tensor]] = None              # depth x [1, cap, mem_D] pre-allocated
     labels = None

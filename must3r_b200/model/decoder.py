@@ -216,9 +216,14 @@ class MUSt3R(nn.Module):
         for i in range(G):
             Bi, n, N, Denc = x[i].shape
             assert Bi == B and Denc == self.enc_embed_dim
-            ts = true_shape[i].reshape(B * n, 2)
-            assert bool((ts == ts[:1]).all()), 'true_shape must be all identical'   # head.py:31
-            H, W = (int(v) for v in ts[0].tolist())
+            hw = getattr(true_shape[i], "_m3r_hw", None)
+            if hw is None:
+                # like the reference (head.py:31-32) this reads true_shape on the host: a device sync when it is a CUDA
+                # tensor.  must3r_b200.engine attaches the host copy as `_m3r_hw` so the launch thread never stalls.
+                ts = true_shape[i].reshape(B * n, 2)
+                assert bool((ts == ts[:1]).all()), 'true_shape must be all identical'   # head.py:31
+                hw = tuple(int(v) for v in ts[0].tolist())
+            H, W = hw
             if self.landscape_only and H > W:
                 raise NotImplementedError("landscape_only=True with portrait views: load_model converts the head to "
                                           "landscape_only=False (must3r/model/__init__.py:55); do the same here")

@@ -22,6 +22,32 @@ for rep in range(3):
     ev[0].record(); m2, _ = dec(x[None, 10:11], pos[None, 10:11], ts[None, 10:11], mem); ev[1].record()
 torch.cuda.synchronize()
 print(f"update step (1 view, M=10): {ev[0].elapsed_time(ev[1]):.3f} ms", flush=True)
+import time
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for rep in range(5):
+    m2, _ = dec(x[None, 10:11], pos[None, 10:11], ts[None, 10:11], mem)
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+t2 = time.perf_counter()
+# split the host time: C call (kernel enqueue from C++) vs Python wrapper around it
+from must3r_b200 import _lib as _L
+_orig = _L.lib().m3r_decoder_forward
+_acc = [0.0, 0]
+def _timed(*a):
+    t = time.perf_counter(); r = _orig(*a); _acc[0] += time.perf_counter() - t; _acc[1] += 1; return r
+class _Proxy:
+    def __getattr__(self, n): return _timed if n == "m3r_decoder_forward" else getattr(_L._lib, n)
+_real = _L.lib
+_L.lib = lambda: _Proxy()
+import must3r_b200.model.decoder as _D
+_D._lib.lib = _L.lib
+for rep in range(5):
+    m2, _ = dec(x[None, 10:11], pos[None, 10:11], ts[None, 10:11], mem)
+torch.cuda.synchronize()
+_L.lib = _real; _D._lib.lib = _real
+print(f"  of which inside m3r_decoder_forward (C++ enqueue of ~220 launches): {_acc[0] / max(_acc[1], 1) * 1e3:.3f} ms", flush=True)
+print(f"host time per update call (enqueue only): {(t1 - t0) / 5 * 1e3:.3f} ms; with final sync: {(t2 - t0) / 5 * 1e3:.3f} ms", flush=True)
 for rep in range(2):
     ev[2].record(); dec(x[None, :8], pos[None, :8], ts[None, :8], mem, render=True); ev[3].record()
 torch.cuda.synchronize()
