@@ -230,7 +230,7 @@ extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int6
   if (M <= 0) return 0;
   if (D % 4 || D > 2048 || ldx % 4 || (add && ldadd % 4) || ldo % 4) return set_error("layernorm: D=%d must be a multiple of 4, <= 2048, 16B-aligned rows", D);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const int wpb = 8;
+  const int wpb = M <= 4096 ? 4 : 8;          // small row counts: more, smaller blocks cover more SMs
   const int grid = (M + wpb - 1) / wpb;
   ProfScope prof(PROF_LN, 0.0, (double)M * D * (4.0 + (add ? 4.0 : 0.0) + (out_dtype ? 2.0 : 4.0)), s);
   if (D <= 1024)

@@ -465,9 +465,10 @@ extern "C" int m3r_gemm(const m3r_gemm_args* a, void* stream) {
   // Tile-width heuristic: widest BN that still yields about one wave of CTAs.
   const int tiles_m = (a->M + BM - 1) / BM;
   const int sms = num_sms();
+  // (profiles/r01_small_gemm_tiles.txt: at M=768, BN=128 wins from ~100 tiles up, BN=64 below)
   int bn = 64;
   if (a->N % 256 == 0 && tiles_m * (a->N / 256) >= sms) bn = 256;
-  else if (a->N % 128 == 0 && tiles_m * (a->N / 128) >= sms) bn = 128;
+  else if (a->N % 128 == 0 && tiles_m * (a->N / 128) >= (sms * 2) / 3) bn = 128;
   {
     // CTA-pair kernel for problems with at least one 256x256 tile per SM pair.  Measured (profiles/r01_run13_gemm_pair.log):
     // +7..+20 % for K >= 1024, -1..-4 % for K = 768 (epilogue-bound tiles) -> used for K >= 1024; M3R_GEMM_PAIR=0/2

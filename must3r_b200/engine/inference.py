@@ -37,17 +37,19 @@ def _to_out(v, outdevice):
 
 
 def _with_host_shape(true_shape_group, device):
-    """true_shape [n,2] of one aspect-ratio group -> [1,n,2] on `device`.  When the caller's tensor lives on the host (the
-    usual case: it comes from the image loader) its (H, W) is attached as `_m3r_hw`, which lets the CUDA decoder skip the
-    device->host read the reference performs in every call (must3r/model/blocks/head.py:31-32)."""
-    out = true_shape_group.unsqueeze(0).to(device)
-    if not true_shape_group.is_cuda:
-        rows = true_shape_group.reshape(-1, 2)
-        assert bool((rows == rows[:1]).all()), 'true_shape must be all identical'
-        try:
-            out._m3r_hw = tuple(int(v) for v in rows[0].tolist())
-        except Exception:  # noqa: BLE001  (tensor subclasses that refuse attributes)
-            pass
+    """true_shape [n,2] of one aspect-ratio group -> [1,n,2] for the decoder.  The decoder only ever reads true_shape on
+    the host (must3r/model/blocks/head.py:31-32), so a host tensor (the usual case: it comes from the image loader) is
+    passed through as is - moving it to the GPU, as the reference engine does, costs a blocking pageable H2D copy per
+    decoder call - and its (H, W) is attached as `_m3r_hw` so the CUDA decoder does no device->host read either."""
+    if true_shape_group.is_cuda:
+        return true_shape_group.unsqueeze(0).to(device)
+    out = true_shape_group.unsqueeze(0)
+    rows = true_shape_group.reshape(-1, 2)
+    assert bool((rows == rows[:1]).all()), 'true_shape must be all identical'
+    try:
+        out._m3r_hw = tuple(int(v) for v in rows[0].tolist())
+    except Exception:  # noqa: BLE001  (tensor subclasses that refuse attributes)
+        pass
     return out
 
 

@@ -6,6 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from must3r_b200 import ops  # noqa: E402
 
 once = "--once" in sys.argv
+warm = "--warm" in sys.argv      # do not flush L2 between iterations (operands stay L2-resident like inside a step)
 which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["attn", "gemm"]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -16,7 +17,8 @@ def timeit(fn, iters=10):
         torch.cuda.synchronize(); return 0.0
     ts = []
     for _ in range(iters):
-        flush.zero_()
+        if not warm:
+            flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
@@ -72,3 +74,21 @@ if "sweep" in which:
         ms0 = timeit(lambda: ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk), iters=7)
         res.sort()
         print(f"sweep {name:20s} default {ms0*1e3:7.1f} us | best " + "  ".join(f"qt{q_}s{s_}:{m*1e3:.1f}" for m, q_, s_ in res[:5]), flush=True)
+
+if "small" in which:
+    import os as _os
+    for name, (M, N, K) in {"dec qkv 1v": (768, 2304, 768), "dec proj 1v": (768, 768, 768), "dec kv 1v": (768, 1536, 768),
+                            "dec fc1 1v": (768, 3072, 768), "dec fc2 1v": (768, 768, 3072), "224 proj 1v": (196, 768, 768), "224 fc1 1v": (196, 3072, 768)}.items():
+        a = torch.randn(M, K, device="cuda").to(dt); w = torch.randn(N, K, device="cuda").to(dt)
+        out = torch.empty(M, N, device="cuda", dtype=dt)
+        res = []
+        for bn in (64, 128, 256):
+            if N % bn: continue
+            _os.environ["M3R_GEMM_BN"] = str(bn)
+            res.append((timeit(lambda: ops.linear(a, w, None, out=out), iters=15), bn))
+        _os.environ.pop("M3R_GEMM_BN")
+        print(f"small gemm {name:12s} M={M} N={N} K={K}: " + "  ".join(f"BN{b}:{m*1e3:.1f}us" for m, b in res), flush=True)
+    x = torch.randn(768, 768, device="cuda"); g = torch.ones(768, device="cuda"); b = torch.zeros(768, device="cuda")
+    print(f"layernorm 768x768 -> 16 bit: {timeit(lambda: ops.layernorm(x, g, b, 1e-6, out_dtype=dt), iters=15)*1e3:.1f} us", flush=True)
+    x = torch.randn(15360, 768, device="cuda")
+    print(f"layernorm 15360x768 -> 16 bit: {timeit(lambda: ops.layernorm(x, g, b, 1e-6, out_dtype=dt), iters=15)*1e3:.1f} us", flush=True)
