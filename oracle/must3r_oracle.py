@@ -41,6 +41,7 @@ class EncoderConfig:
     rope_base: float = 100.0
     rope_f0: float = 1.0
     ln_eps: float = 1e-6
+    patch_embed: str = "PatchEmbedDust3R"     # or 'ManyAR_PatchEmbed' (dust3r/dust3r/patch_embed.py:13-16)
 
 
 @dataclass
@@ -165,10 +166,30 @@ def patch_embed(sd: Dict[str, Tensor], img: Tensor, patch: int) -> Tuple[Tensor,
     return x, pos.expand(V, -1, -1).clone()
 
 
+def patch_embed_many_ar(sd: Dict[str, Tensor], img: Tensor, true_shape: Tensor, patch: int) -> Tuple[Tensor, Tensor]:
+    """ManyAR_PatchEmbed.forward (dust3r/dust3r/patch_embed.py:42-70): the batch is stored landscape (W >= H); views whose
+    true_shape is portrait are transposed before the projection and get the positions of the transposed grid."""
+    V, C, H, W = img.shape
+    assert W >= H, f"img should be in landscape mode, but got {W=} {H=}"
+    assert tuple(true_shape.shape) == (V, 2)
+    n_tok = (H // patch) * (W // patch)
+    x = img.new_zeros((V, n_tok, sd["patch_embed.proj.bias"].shape[0]))
+    pos = torch.zeros((V, n_tok, 2), dtype=torch.int64, device=img.device)
+    portrait = true_shape[:, 1] < true_shape[:, 0]
+    if bool((~portrait).any()):
+        x[~portrait], pos[~portrait] = patch_embed(sd, img[~portrait], patch)
+    if bool(portrait.any()):
+        x[portrait], pos[portrait] = patch_embed(sd, img[portrait].swapaxes(-1, -2), patch)
+    return x, pos
+
+
 def encoder_forward(sd: Dict[str, Tensor], cfg: EncoderConfig, img: Tensor, true_shape: Tensor
                     ) -> Tuple[Tensor, Tensor]:
     """Dust3rEncoder.forward, must3r/model/encoder.py:46-52 (always fp32)."""
-    x, pos = patch_embed(sd, img.float(), cfg.patch_size)
+    if cfg.patch_embed == "ManyAR_PatchEmbed":
+        x, pos = patch_embed_many_ar(sd, img.float(), true_shape, cfg.patch_size)
+    else:
+        x, pos = patch_embed(sd, img.float(), cfg.patch_size)
     for i in range(cfg.depth):
         p = f"blocks_enc.{i}."
         # Block.forward, must3r/model/blocks/layers.py:51-54

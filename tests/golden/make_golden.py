@@ -114,6 +114,12 @@ def tiny_model_golden():
     mem2, pms = dec([xp[None, :1], xl[None, :1]], [pp[None, :1], pl[None, :1]], [ts_p[None, :1], ts_l[None, :1]], mem)
     out["list.pm2"], out["list.pm3"] = pms[0].numpy(), pms[1].numpy()
     mem_arrays("list.final", mem2, out)
+    # ManyAR patch embedding: landscape-stored batch with one portrait view (dust3r/dust3r/patch_embed.py:32-70)
+    enc_m, _ = build_ref({**TINY_ENC, "patch_embed": "ManyAR_PatchEmbed"}, TINY_DEC, seed=7)
+    imgs_m, _ = syn.synthetic_views(3, H, W, seed=15)
+    ts_m = torch.tensor([[H, W], [W, H], [H, W]], dtype=torch.int64)
+    xm, pm_ = enc_m(imgs_m, ts_m)
+    out["manyar.enc_x"], out["manyar.enc_pos"] = xm.numpy(), pm_.numpy()
     # postprocess (engine/inference.py:16-27)
     pp_out = ref_engine.postprocess(torch.from_numpy(out["kv.pm_render"]), ActivationType.NORM_EXP)
     for k, v in pp_out.items():

@@ -170,6 +170,19 @@ def test_engine_on_cuda_vs_reference_engine(dtype):
     assert rel(pm0.cpu(), g["inference.pm0"]) < tol and rel(pm.cpu(), g["inference.pm"]) < tol
 
 
+@pytest.mark.parametrize("dtype", DT)
+def test_many_ar_patch_embed_vs_reference(dtype):
+    """ManyAR_PatchEmbed (landscape-stored batch with a portrait view, dust3r/dust3r/patch_embed.py:32-70)."""
+    set_precision(dtype)
+    g = load_golden("tiny_model.npz")
+    enc, _ = tiny_cuda(7, dict(patch_embed="ManyAR_PatchEmbed"))
+    imgs, _ = syn.synthetic_views(3, 32, 48, seed=15)
+    ts = torch.tensor([[32, 48], [48, 32], [32, 48]], dtype=torch.int64)
+    x, pos = enc(imgs.cuda(), ts.cuda())
+    assert rel(x.cpu(), g["manyar.enc_x"]) < TOL[dtype]
+    assert np.array_equal(pos.cpu().numpy(), g["manyar.enc_pos"])
+
+
 def test_cuda_vs_oracle_same_box():
     """The CPU oracle (pinned to the reference by test_oracle_golden) evaluated on this box vs the CUDA path."""
     set_precision(torch.float16)

@@ -79,6 +79,16 @@ def test_tiny_list_form_two_aspect_ratios():
     check_mem(g, "list.final", mem2)
 
 
+def test_many_ar_patch_embed():
+    g = load_golden("tiny_model.npz")
+    enc, _ = tiny_oracle(7, dict(patch_embed="ManyAR_PatchEmbed"))
+    imgs, _ = syn.synthetic_views(3, 32, 48, seed=15)
+    ts = torch.tensor([[32, 48], [48, 32], [32, 48]], dtype=torch.int64)
+    x, pos = enc(imgs, ts)
+    assert rel(x, g["manyar.enc_x"]) < TOL
+    assert np.array_equal(pos.numpy(), g["manyar.enc_pos"])
+
+
 def test_postprocess():
     g = load_golden("tiny_model.npz")
     out = orc.postprocess(torch.from_numpy(g["kv.pm_render"]))
