@@ -19,9 +19,13 @@
 extern "C" {
 #endif
 
-#define M3R_ABI_VERSION 2
+#define M3R_ABI_VERSION 3
 #define M3R_MAX_PEERS 8
 
+/* m3r_decoder_call.mem_mode (MEMORY_MODES, must3r/model/blocks/layers.py:9) */
+#define M3R_MEM_KV 0
+#define M3R_MEM_NORM_Y 1
+#define M3R_MEM_RAW 2
 /* out_dtype */
 #define M3R_OUT_F32 0
 #define M3R_OUT_16 1
@@ -40,6 +44,9 @@ long long m3r_launch_count(void);
  * other (28 doubles). */
 void m3r_prof_enable(int on);
 int m3r_prof_read(double* out);
+/* Debug hook (tools/trace_attn.py): device buffer of 64 x #CTAs uint64 that subsequent m3r_attention launches fill with
+ * %globaltimer stamps of one softmax thread per CTA (entry, per-tile barrier waits, epilogue, merge); NULL = off. */
+int m3r_debug_attn_trace(void* buf);
 
 /* ---------------------------------------------------------------------------------------------------
  * Linear layer y = act(x W^T + b) (+ residual) on tcgen05 tensor cores.
@@ -93,6 +100,14 @@ int m3r_layernorm(const float* x, int64_t ldx, const float* add, int64_t ldadd, 
 /* fp32 -> 16-bit cast of [M,D] rows (encoder features entering the decoder projector, decoder.py:274). */
 int m3r_cast16(const float* x, int64_t ldx, int32_t M, int32_t D, void* out, int64_t ldo, int32_t is_bf16,
                void* stream);
+
+/* LayerNorm of 16-bit rows -> 16-bit rows (memory_mode 'raw': norm_y applied to the stored tokens at use,
+ * must3r/model/blocks/layers.py:92), and fp32 (x + add) -> 16-bit (what 'raw' stores, layers.py:82-83 after the feedback
+ * offset of decoder.py:323-330). */
+int m3r_layernorm16(const void* x16, int64_t ldx, const float* gamma, const float* beta, float eps, int32_t M, int32_t D,
+                    void* out16, int64_t ldo, int32_t is_bf16, void* stream);
+int m3r_add_cast16(const float* x, int64_t ldx, const float* add, int64_t ldadd, int32_t M, int32_t D, void* out,
+                   int64_t ldo, int32_t is_bf16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * RoPE trig table: tab[t] = (cos, sin)(pos[t,axis] * F0 / base^(d/16)), d<16, for axis y then x.
@@ -239,6 +254,10 @@ typedef struct {
                                       into every rank's memory buffer (fused GEMM -> all-gather over NVLink peer memory) */
   void* const* peer_mem;           /* host array [n_peers * depth]: peer_mem[r * depth + l] = rank r's memory buffer of
                                       level l ([1, cap, 2D] 16-bit), already offset to the row where THIS rank's tokens go */
+  int32_t mem_mode;                /* M3R_MEM_KV: memory rows are K|V (2D wide); M3R_MEM_NORM_Y: rows are norm_y(x) (D wide) and
+                                      K|V are projected at use; M3R_MEM_RAW: rows are x (D wide), norm_y + projection at use
+                                      (must3r/model/blocks/layers.py:81-96).  All widths "2D" above become D for the last two.
+                                      peer output (n_peers > 0) needs M3R_MEM_KV. */
 } m3r_decoder_call;
 
 int64_t m3r_decoder_workspace_bytes(const m3r_decoder_weights* w, const m3r_decoder_call* call);

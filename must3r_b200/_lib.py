@@ -50,6 +50,7 @@ class AttnArgs(C.Structure):
 SIGNATURES = {
     "m3r_last_error": (C.c_char_p, []),
     "m3r_abi_version": (C.c_int, []),
+    "m3r_debug_attn_trace": (C.c_int, [C.c_void_p]),
     "m3r_launch_count": (C.c_longlong, []),
     "m3r_prof_enable": (None, [C.c_int]),
     "m3r_prof_read": (C.c_int, [C.POINTER(C.c_double)]),
@@ -57,6 +58,10 @@ SIGNATURES = {
     "m3r_layernorm": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "m3r_cast16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
+    "m3r_layernorm16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
+                                  C.c_int64, C.c_int32, C.c_void_p]),
+    "m3r_add_cast16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64,
+                                 C.c_int32, C.c_void_p]),
     "m3r_rope_table": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "m3r_rope_2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                               C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),

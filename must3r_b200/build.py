@@ -34,6 +34,9 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math_off_placeholder"]
+    if os.environ.get("M3R_ATTN_TRACE") == "1":          # debug build: in-kernel %globaltimer stamps (tools/trace_attn.py)
+        flags.append("-DM3R_ATTN_TRACE")
+        force = True
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "must3r_b200.h"))
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]

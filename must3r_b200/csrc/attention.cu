@@ -55,7 +55,11 @@ struct AttnParams {
   int* split_cnt;            // [B, H, ceil(Nq/128)] arrival counters (zero on entry, reset by the last arriver)
   int H;
   long long rows_total;      // B * Nq
+  unsigned long long* trace; // debug only (m3r_debug_attn_trace): per-CTA clock stamps, 64 words per CTA; normally null
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 
 struct TileIt {
   int seg, t;          // current tile
@@ -64,26 +68,42 @@ struct TileIt {
   bool mask;           // needs element masking
 };
 
-// Enumerate key tiles, skipping the ones entirely inside the skip range. Every warp role runs the same walk.
-struct TileWalk {
+// Key tiles in visiting order, without the ones entirely inside the skip range [lo, hi) (a view's own new tokens:
+// never loaded nor multiplied).  Closed form: the fully masked tiles are one contiguous run [s0, s0 + ns) of the linear
+// tile index (segment 0 tiles, then segment 1 tiles), so tile i of the visit is linear tile i (+ ns past the run).
+// Every warp role maps indices the same way; no per-thread walk over the (possibly thousands of) tiles.
+struct TileMap {
   int nk0, nk1, lo, hi;
-  int seg, t;
-  __device__ TileWalk(int nk0_, int nk1_, int lo_, int hi_) : nk0(nk0_), nk1(nk1_), lo(lo_), hi(hi_), seg(0), t(0) {}
-  __device__ bool next(TileIt& it) {
-    while (seg < 2) {
-      const int n = seg == 0 ? nk0 : nk1;
-      if (t * AT_BN >= n) { ++seg; t = 0; continue; }
-      const int l0 = t * AT_BN;
-      const int l1 = min(l0 + AT_BN, n);
-      const int base = seg == 0 ? 0 : nk0;
-      const int g0 = base + l0, g1 = base + l1;
-      const int cur_t = t++;
-      if (g0 >= lo && g1 <= hi) continue;     // fully masked: never loaded nor multiplied
-      it.seg = seg; it.t = cur_t; it.g0 = g0; it.nvalid = l1 - l0;
-      it.mask = (l1 - l0 < AT_BN) || (g0 < hi && g1 > lo);
-      return true;
+  int T0, s0, ns, n_all;
+  __device__ static void masked_run(int n, int base, int T, int lo, int hi, int& a, int& c) {
+    const int l = lo - base, h = hi - base;
+    a = l <= 0 ? 0 : (l + AT_BN - 1) / AT_BN;                 // first tile with g0 >= lo
+    const int b = h >= n ? T : (h <= 0 ? 0 : h / AT_BN);       // one past the last tile with g1 <= hi
+    c = max(0, min(b, T) - a);
+  }
+  __device__ TileMap(int nk0_, int nk1_, int lo_, int hi_) : nk0(nk0_), nk1(nk1_), lo(lo_), hi(hi_) {
+    T0 = (nk0 + AT_BN - 1) / AT_BN;
+    const int T1 = (nk1 + AT_BN - 1) / AT_BN;
+    int a0 = 0, c0 = 0, a1 = 0, c1 = 0;
+    if (hi > lo) {
+      masked_run(nk0, 0, T0, lo, hi, a0, c0);
+      masked_run(nk1, nk0, T1, lo, hi, a1, c1);
     }
-    return false;
+    s0 = c0 > 0 ? a0 : T0 + a1;       // (a range covering both segments ends segment 0 and starts segment 1: contiguous)
+    ns = c0 + c1;
+    n_all = T0 + T1 - ns;
+  }
+  __device__ __forceinline__ TileIt get(int i) const {
+    const int u = i + (i >= s0 ? ns : 0);
+    TileIt it;
+    it.seg = u >= T0 ? 1 : 0;
+    it.t = u - (it.seg ? T0 : 0);
+    const int n = it.seg ? nk1 : nk0;
+    const int l0 = it.t * AT_BN;
+    it.nvalid = min(AT_BN, n - l0);
+    it.g0 = (it.seg ? nk0 : 0) + l0;
+    it.mask = (it.nvalid < AT_BN) || (it.g0 < hi && it.g0 + it.nvalid > lo);
+    return it;
   }
 };
 
@@ -163,6 +183,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* o_done = p_full + 2;       // [2] MMA -> softmax x : P_x(j) V(j) accumulated into O_x, P columns free again
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
+#ifdef M3R_ATTN_TRACE
+  const unsigned long long t_entry = p.trace ? gtime_ns() : 0ull;
+#define M3R_TR(...) __VA_ARGS__
+#else
+#define M3R_TR(...)
+#endif
   const int warp = threadIdx.x >> 5;
   const int qblk = blockIdx.x, h = blockIdx.y;
   const int b = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
@@ -174,8 +200,8 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const int nqt = (QT == 2 && q0 + AT_BM < p.Nq) ? 2 : 1;
 
   // this CTA's share [i0, i1) of the enumerated key tiles
-  int n_all = 0;
-  { TileWalk w(p.Nk0, p.Nk1, lo, hi); TileIt it; while (w.next(it)) ++n_all; }
+  const TileMap tiles(p.Nk0, p.Nk1, lo, hi);
+  const int n_all = tiles.n_all;
   const int chunk = (n_all + p.splits - 1) / p.splits;
   const int i0 = split * chunk;
   const int i1 = min(n_all, i0 + chunk);
@@ -202,24 +228,18 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (elect_one() && n_tiles > 0) {
       mbar_arrive_expect_tx(q_full, nqt * TILE_BYTES);
       for (int x = 0; x < nqt; ++x) tma_load_3d(sQ + x * TILE_BYTES, &tmQ, q_full, h * HD, q0 + x * AT_BM, b);
-      TileWalk walk(p.Nk0, p.Nk1, lo, hi);
-      TileIt it;
-      int i = 0, j = 0;
-      while (walk.next(it)) {
-        if (i >= i0 && i < i1) {
-          const int st = j % KS;
-          const uint32_t ph = (j / KS) & 1;
-          const CUtensorMap* mk = it.seg == 0 ? &tmK0 : &tmK1;
-          const CUtensorMap* mv = it.seg == 0 ? &tmV0 : &tmV1;
-          mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
-          tma_load_3d(sK + st * TILE_BYTES, mk, &k_full[st], h * HD, it.t * AT_BN, kvb);
-          mbar_wait(&v_empty[st], ph ^ 1);
-          mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
-          tma_load_3d(sV + st * TILE_BYTES, mv, &v_full[st], h * HD, it.t * AT_BN, kvb);
-          ++j;
-        }
-        ++i;
+      for (int j = 0; j < n_tiles; ++j) {
+        const TileIt it = tiles.get(i0 + j);
+        const int st = j % KS;
+        const uint32_t ph = (j / KS) & 1;
+        const CUtensorMap* mk = it.seg == 0 ? &tmK0 : &tmK1;
+        const CUtensorMap* mv = it.seg == 0 ? &tmV0 : &tmV1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], TILE_BYTES);
+        tma_load_3d(sK + st * TILE_BYTES, mk, &k_full[st], h * HD, it.t * AT_BN, kvb);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], TILE_BYTES);
+        tma_load_3d(sV + st * TILE_BYTES, mv, &v_full[st], h * HD, it.t * AT_BN, kvb);
       }
     }
   } else if (warp >= MMA_WARP && warp < MMA_WARP + nqt) {
@@ -286,13 +306,15 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     float l_run = 0.f;
     const PolyC polyc = make_polyc();
 
-    TileWalk walk(p.Nk0, p.Nk1, lo, hi);
-    TileIt it;
-    int i = 0, j = 0;
-    while (walk.next(it)) {
-      if (i < i0 || i >= i1) { ++i; continue; }
-      ++i;
+    M3R_TR(unsigned long long* tr = nullptr;
+           if (p.trace && row == 0 && x == 0)
+             tr = p.trace + 64ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+           if (tr) { tr[0] = t_entry; tr[1] = gtime_ns(); tr[2] = smid(); tr[3] = (unsigned long long)n_tiles; })
+    int j = 0;
+    for (; j < n_tiles; ++j) {
+      const TileIt it = tiles.get(i0 + j);
       mbar_wait(&s_full[x], j & 1);
+      M3R_TR(if (tr && j < 12) tr[8 + 4 * j] = gtime_ns();)
       tc_fence_after();
       uint32_t raw[128];
       tmem_ld32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
@@ -302,6 +324,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&s_free[x]);                     // Q K^T of the next tile may overwrite S now
+      M3R_TR(if (tr && j < 12) tr[9 + 4 * j] = gtime_ns();)
       if (it.mask) {
 #pragma unroll
         for (int c = 0; c < 128; ++c) {
@@ -331,6 +354,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         // P V (j-1) must have consumed the P columns (and landed in O) before they are rewritten / O is rescaled.
         // Every phase of o_done is waited for, in order, so the parity wait is exact.
         mbar_wait(&o_done[x], (j - 1) & 1);
+        M3R_TR(if (tr && j < 12) tr[10 + 4 * j] = gtime_ns();)
         tc_fence_after();
         if (__any_sync(0xffffffffu, refresh)) {
 #pragma unroll 1
@@ -375,9 +399,10 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[x]);
+      M3R_TR(if (tr && j < 12) tr[11 + 4 * j] = gtime_ns();)
       l_run += (r0 + r1) + (r2 + r3);
-      ++j;
     }
+    M3R_TR(if (tr) tr[4] = gtime_ns();)
 
     // ---- epilogue: wait for the last P V, normalise, store
     uint32_t accr[HD];
@@ -408,64 +433,92 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
           w.w = packp<BF16>(acc[8 * t + 6] * inv, acc[8 * t + 7] * inv);
           o4[t] = w;
         }
-      } else {
-        float4* o4 = reinterpret_cast<float4*>(p.part_o + ((long long)split * p.rows_total + grow) * (p.H * HD) + h * HD);
-#pragma unroll
-        for (int t = 0; t < 16; ++t) o4[t] = make_float4(acc[4 * t], acc[4 * t + 1], acc[4 * t + 2], acc[4 * t + 3]);
-        float2* ml = reinterpret_cast<float2*>(p.part_ml) + ((long long)split * p.rows_total + grow) * p.H + h;
-        *ml = make_float2(m_used == -INFINITY ? -INFINITY : m_used * p.sl2, l_run);
       }
     }
+    // key-range splits: unnormalised partial (O, m, l) of this CTA.  Layout [split][unit = (b, h, query tile)][16 column
+    // chunks][128 rows] float4 (and [split][unit][128 rows] float2): lanes are consecutive rows, so both these stores and
+    // the merge's loads are fully coalesced 512 B requests.
+    const int n_qtiles = (p.Nq + AT_BM - 1) / AT_BM;
+    const long long unit = ((long long)b * p.H + h) * n_qtiles + (q0 / AT_BM + x);
+    const long long n_units = (long long)gridDim.z / p.splits * p.H * n_qtiles;
+    if (p.splits > 1) {
+      float4* o4 = reinterpret_cast<float4*>(p.part_o) + ((long long)split * n_units + unit) * (16 * AT_BM) + row;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) o4[t * AT_BM] = make_float4(acc[4 * t], acc[4 * t + 1], acc[4 * t + 2], acc[4 * t + 3]);
+      reinterpret_cast<float2*>(p.part_ml)[((long long)split * n_units + unit) * AT_BM + row] =
+          make_float2(m_used == -INFINITY ? -INFINITY : m_used * p.sl2, l_run);
+    }
+    M3R_TR(if (tr) tr[5] = gtime_ns();)
     if (p.splits > 1) {
       // ---- merge of the key-range splits by the last CTA to finish this (batch, head, query tile):
       // out = sum_s O_s 2^(m_s - m) / sum_s l_s 2^(m_s - m).  No extra kernel launch on the one-view-per-step chain.
       __shared__ int s_last[2];
       __threadfence();                                              // partials visible device-wide
       asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");    // the 4 warps of this warpgroup
-      const int n_qtiles = (p.Nq + AT_BM - 1) / AT_BM;
-      int* cnt = p.split_cnt + ((long long)b * p.H + h) * n_qtiles + (q0 / AT_BM + x);
+      int* cnt = p.split_cnt + unit;
       if (row == 0) {
         const int prev = atomicAdd(cnt, 1);
         s_last[x] = (prev == p.splits - 1);
         if (prev == p.splits - 1) *cnt = 0;                         // self-cleaning for the next launch
       }
       asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
-      if (s_last[x] && q_idx < p.Nq) {
+      if (s_last[x]) {
         __threadfence();
-        const long long grow = (long long)b * p.Nq + q_idx;
+        const float2* mlp = reinterpret_cast<const float2*>(p.part_ml) + unit * AT_BM + row;
+        const float4* op = reinterpret_cast<const float4*>(p.part_o) + unit * (16 * AT_BM) + row;
+        const long long ml_stride = n_units * AT_BM, o_stride = n_units * (16 * AT_BM);
         float m = -INFINITY;
-        for (int sp = 0; sp < p.splits; ++sp)
-          m = fmaxf(m, __ldcg(p.part_ml + (((long long)sp * p.rows_total + grow) * p.H + h) * 2));
+#pragma unroll 4
+        for (int sp = 0; sp < p.splits; ++sp) m = fmaxf(m, __ldcg(mlp + sp * ml_stride).x);
         float l = 0.f;
+        const long long grow = (long long)b * p.Nq + q_idx;
+        // a quarter of the 64 columns at a time: 4 splits x 4 float4 loads in flight per thread, few L2 round trips
+#pragma unroll 1
+        for (int qd = 0; qd < 4; ++qd) {
+          float a16[16];
 #pragma unroll
-        for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-        for (int sp = 0; sp < p.splits; ++sp) {
-          const float2 ml = __ldcg(reinterpret_cast<const float2*>(p.part_ml) + ((long long)sp * p.rows_total + grow) * p.H + h);
-          const float wgt = (ml.x == -INFINITY) ? 0.f : ex2(ml.x - m);
-          l += ml.y * wgt;
-          const float4* o = reinterpret_cast<const float4*>(p.part_o + ((long long)sp * p.rows_total + grow) * (p.H * HD) + h * HD);
+          for (int d = 0; d < 16; ++d) a16[d] = 0.f;
+          for (int sp0 = 0; sp0 < p.splits; sp0 += 4) {
+            float4 v[4][4];
+            float w[4];
 #pragma unroll
-          for (int t = 0; t < 16; ++t) {
-            const float4 v = __ldcg(o + t);
-            acc[4 * t] = fmaf(v.x, wgt, acc[4 * t]); acc[4 * t + 1] = fmaf(v.y, wgt, acc[4 * t + 1]);
-            acc[4 * t + 2] = fmaf(v.z, wgt, acc[4 * t + 2]); acc[4 * t + 3] = fmaf(v.w, wgt, acc[4 * t + 3]);
+            for (int u = 0; u < 4; ++u) {
+              const int sp = min(sp0 + u, p.splits - 1);
+              const float2 ml = __ldcg(mlp + sp * ml_stride);
+              w[u] = (sp0 + u < p.splits && ml.x != -INFINITY) ? ex2(ml.x - m) : 0.f;
+              if (qd == 0) l += ml.y * w[u];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) v[u][t] = __ldcg(op + sp * o_stride + (qd * 4 + t) * AT_BM);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                a16[4 * t] = fmaf(v[u][t].x, w[u], a16[4 * t]); a16[4 * t + 1] = fmaf(v[u][t].y, w[u], a16[4 * t + 1]);
+                a16[4 * t + 2] = fmaf(v[u][t].z, w[u], a16[4 * t + 2]); a16[4 * t + 3] = fmaf(v[u][t].w, w[u], a16[4 * t + 3]);
+              }
+            }
           }
-        }
-        const float inv = l > 0.f ? 1.0f / l : 0.f;
-        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD);
+          const float inv = l > 0.f ? 1.0f / l : 0.f;      // l is complete after the first quarter
+          if (q_idx < p.Nq) {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD + qd * 16);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          uint4 w;
-          w.x = packp<BF16>(acc[8 * t] * inv, acc[8 * t + 1] * inv);
-          w.y = packp<BF16>(acc[8 * t + 2] * inv, acc[8 * t + 3] * inv);
-          w.z = packp<BF16>(acc[8 * t + 4] * inv, acc[8 * t + 5] * inv);
-          w.w = packp<BF16>(acc[8 * t + 6] * inv, acc[8 * t + 7] * inv);
-          o4[t] = w;
+            for (int t = 0; t < 2; ++t) {
+              uint4 wv;
+              wv.x = packp<BF16>(a16[8 * t] * inv, a16[8 * t + 1] * inv);
+              wv.y = packp<BF16>(a16[8 * t + 2] * inv, a16[8 * t + 3] * inv);
+              wv.z = packp<BF16>(a16[8 * t + 4] * inv, a16[8 * t + 5] * inv);
+              wv.w = packp<BF16>(a16[8 * t + 6] * inv, a16[8 * t + 7] * inv);
+              o4[t] = wv;
+            }
+          }
         }
       }
     }
   }
 
+  M3R_TR(if (p.trace && threadIdx.x == 0)
+           p.trace[64ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) + 6] = gtime_ns();)
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
@@ -499,6 +552,20 @@ static size_t g_split_cap = 0;
 }  // namespace m3r
 
 // Number of fp32 scratch elements m3r_attention may need for a problem (0 if it will not split).
+static unsigned long long* g_attn_trace = nullptr;
+// Debug hook (tools/trace_attn.py): device buffer of 64 x #CTAs uint64 that the next m3r_attention launches fill with
+// %globaltimer stamps of softmax warp 0 (entry, per-tile barrier waits, epilogue, merge); nullptr switches it off.
+// Compiled in only with -DM3R_ATTN_TRACE (M3R_ATTN_TRACE=1 python -m must3r_b200.build): the stamps cost registers.
+extern "C" int m3r_debug_attn_trace(void* buf) {
+#ifdef M3R_ATTN_TRACE
+  g_attn_trace = reinterpret_cast<unsigned long long*>(buf);
+  return 0;
+#else
+  (void)buf;
+  return m3r::set_error("attention trace not compiled in (build with M3R_ATTN_TRACE=1)");
+#endif
+}
+
 extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   using namespace m3r;
   if (!a || !a->Q || !a->K0 || !a->V0 || !a->O) return set_error("attention: null pointer");
@@ -556,13 +623,14 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   p.splits = splits; p.sl2 = a->scale * 1.4426950408889634f;
   p.O = a->O; p.ldo = a->ldo; p.H = a->H; p.rows_total = (long long)a->B * a->Nq;
   p.part_o = nullptr; p.part_ml = nullptr; p.split_cnt = nullptr;
+  p.trace = g_attn_trace;
   if (splits > 1) {
     // scratch layout: [4096 arrival counters | partial O | partial (m, l)].  The counters sit at a fixed place, are
     // zeroed once when the buffer is (re)allocated and every launch leaves them zero again (last arriver resets).
     constexpr size_t CNT = 4096;
     const size_t n_cnt = (size_t)a->B * a->H * ((a->Nq + AT_BM - 1) / AT_BM);
     if (n_cnt > CNT) return set_error("attention: too many (batch, head, tile) groups for the split path");
-    const size_t need = CNT + (size_t)splits * p.rows_total * a->H * (HD + 2);
+    const size_t need = CNT + (size_t)splits * n_cnt * AT_BM * (HD + 2);     // partial O + (m, l), padded to whole query tiles
     if (need > g_split_cap) {
       if (g_split_buf) cudaFreeAsync(g_split_buf, cs);
       g_split_buf = nullptr; g_split_cap = 0;
@@ -573,7 +641,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     }
     p.split_cnt = reinterpret_cast<int*>(g_split_buf);
     p.part_o = g_split_buf + CNT;
-    p.part_ml = p.part_o + (size_t)splits * p.rows_total * a->H * HD;
+    p.part_ml = p.part_o + (size_t)splits * n_cnt * AT_BM * HD;
   }
   {
     const double nk_eff = (double)(a->Nk0 + a->Nk1 - a->skip_len);

@@ -14,8 +14,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // One warp per row; the row lives in registers (D <= 32 * 4 * MAXV). Two-pass mean / variance like torch.
-template <int MAXV>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long ldx,
+template <int MAXV, bool IN16>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ xv, long long ldx,
                                                         const float* __restrict__ add, long long ldadd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int M, int D, void* __restrict__ out, long long ldo,
@@ -26,7 +26,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;  // float4 per row
-  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+  const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xv) + (IN16 ? 0 : (long long)row * ldx));
+  const uint2* xh = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(xv) + (IN16 ? (long long)row * ldx : 0));
   const float4* ar = add ? reinterpret_cast<const float4*>(add + (long long)row * ldadd) : nullptr;
   float4 v[MAXV];
   float s = 0.f;
@@ -34,7 +35,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + i * 32;
     if (idx < nv) {
-      float4 t = xr[idx];
+      float4 t;
+      if (IN16) {
+        const uint2 h = xh[idx];
+        t = make_float4(unpack16_lo(h.x, is_bf16), unpack16_hi(h.x, is_bf16), unpack16_lo(h.y, is_bf16), unpack16_hi(h.y, is_bf16));
+      } else {
+        t = xr[idx];
+      }
       if (ar) { const float4 a = ar[idx]; t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
       v[i] = t;
       s += (t.x + t.y) + (t.z + t.w);
@@ -77,7 +84,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ x, long long ldx, int M, int D,
+__global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ x, long long ldx,
+                                                     const float* __restrict__ add, long long ldadd, int M, int D,
                                                      uint16_t* __restrict__ out, long long ldo, int is_bf16) {
   const int nv = D >> 2;
   const long long total = (long long)M * nv;
@@ -85,7 +93,11 @@ __global__ void __launch_bounds__(256) cast16_kernel(const float* __restrict__ x
   griddep_launch();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int row = int(i / nv), c = int(i % nv);
-    const float4 t = reinterpret_cast<const float4*>(x + (long long)row * ldx)[c];
+    float4 t = reinterpret_cast<const float4*>(x + (long long)row * ldx)[c];
+    if (add) {
+      const float4 a = reinterpret_cast<const float4*>(add + (long long)row * ldadd)[c];
+      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    }
     uint2 w;
     w.x = pack16(t.x, t.y, is_bf16);
     w.y = pack16(t.z, t.w, is_bf16);
@@ -234,20 +246,47 @@ extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int6
   const int grid = (M + wpb - 1) / wpb;
   ProfScope prof(PROF_LN, 0.0, (double)M * D * (4.0 + (add ? 4.0 : 0.0) + (out_dtype ? 2.0 : 4.0)), s);
   if (D <= 1024)
-    launch_pdl(layernorm_kernel<8>, dim3(grid), dim3(wpb * 32), 0, s, x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
+    launch_pdl(layernorm_kernel<8, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
   else
-    launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(wpb * 32), 0, s, x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
+    launch_pdl(layernorm_kernel<16, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
   return check_launch("layernorm");
+}
+
+extern "C" int m3r_layernorm16(const void* x16, int64_t ldx, const float* gamma, const float* beta, float eps, int32_t M,
+                               int32_t D, void* out16, int64_t ldo, int32_t is_bf16, void* stream) {
+  if (!x16 || !gamma || !beta || !out16) return set_error("layernorm16: null pointer");
+  if (M <= 0) return 0;
+  if (D % 4 || D > 2048 || ldx % 4 || ldo % 4) return set_error("layernorm16: D=%d must be a multiple of 4, <= 2048, 8B-aligned rows", D);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int wpb = M <= 4096 ? 4 : 8;
+  const int grid = (M + wpb - 1) / wpb;
+  ProfScope prof(PROF_LN, 0.0, (double)M * D * 4.0, s);
+  const float* none = nullptr;
+  if (D <= 1024)
+    launch_pdl(layernorm_kernel<8, true>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16);
+  else
+    launch_pdl(layernorm_kernel<16, true>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16);
+  return check_launch("layernorm16");
+}
+
+static int cast16_impl(const float* x, int64_t ldx, const float* add, int64_t ldadd, int32_t M, int32_t D, void* out, int64_t ldo,
+                       int32_t is_bf16, void* stream) {
+  if (!x || !out) return set_error("cast16: null pointer");
+  if (M <= 0) return 0;
+  if (D % 4 || ldx % 4 || ldo % 4 || (add && ldadd % 4)) return set_error("cast16: alignment");
+  launch_pdl(cast16_kernel, dim3(grid_for((long long)M * (D / 4), 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             x, (long long)ldx, add, (long long)ldadd, (int)M, (int)D, reinterpret_cast<uint16_t*>(out), (long long)ldo, (int)is_bf16);
+  return check_launch("cast16");
 }
 
 extern "C" int m3r_cast16(const float* x, int64_t ldx, int32_t M, int32_t D, void* out, int64_t ldo, int32_t is_bf16,
                           void* stream) {
-  if (!x || !out) return set_error("cast16: null pointer");
-  if (M <= 0) return 0;
-  if (D % 4 || ldx % 4 || ldo % 4) return set_error("cast16: alignment");
-  launch_pdl(cast16_kernel, dim3(grid_for((long long)M * (D / 4), 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
-             x, (long long)ldx, (int)M, (int)D, reinterpret_cast<uint16_t*>(out), (long long)ldo, (int)is_bf16);
-  return check_launch("cast16");
+  return cast16_impl(x, ldx, nullptr, 0, M, D, out, ldo, is_bf16, stream);
+}
+
+extern "C" int m3r_add_cast16(const float* x, int64_t ldx, const float* add, int64_t ldadd, int32_t M, int32_t D, void* out,
+                              int64_t ldo, int32_t is_bf16, void* stream) {
+  return cast16_impl(x, ldx, add, ldadd, M, D, out, ldo, is_bf16, stream);
 }
 
 extern "C" int m3r_rope_table(const int64_t* pos, int32_t T, float base, float f0, float* tab, void* stream) {

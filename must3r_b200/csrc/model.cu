@@ -137,8 +137,10 @@ static SideStream g_side;
 
 struct DecWs {
   uint16_t *enc16, *h16, *h16b, *qkv16, *q16, *att16, *mlp16, *kvnew;
+  uint16_t *kvmem, *memln;     // memory_mode norm_y / raw: K|V of the stored memory projected at use; LN_y of raw rows
   float *x, *tmp, *snap, *off, *rope, *headout;
   int64_t M, Nt;
+  int nbm;                     // distinct memory batches behind kvmem (1 when the memory is a stride-0 expand)
   std::vector<int64_t> row0;   // first row of each group
   std::vector<int64_t> tok0;   // first new-token index (per scene) of each group
 };
@@ -173,6 +175,12 @@ static int64_t dec_layout(const m3r_decoder_weights* w, const m3r_decoder_call* 
   } else {
     ws->snap = nullptr; ws->off = nullptr; ws->kvnew = nullptr; ws->h16b = nullptr;
   }
+  ws->kvmem = ws->memln = nullptr; ws->nbm = 0;
+  if (c->mem_mode != M3R_MEM_KV && c->Nm > 0) {
+    ws->nbm = (c->B > 1 && c->mem_bstride_rows == 0) ? 1 : c->B;
+    ws->kvmem = a.take<uint16_t>((int64_t)ws->nbm * c->Nm * 2 * D);
+    if (c->mem_mode == M3R_MEM_RAW) ws->memln = a.take<uint16_t>((int64_t)ws->nbm * c->Nm * D);
+  }
   return a.off + 256;
 }
 
@@ -193,6 +201,8 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   if (!c->render && !c->mem_out) return set_error("decoder_forward: mem_out missing");
   if (c->n_peers < 0 || c->n_peers > M3R_MAX_PEERS || (c->n_peers > 0 && (!c->peer_mem || !c->new_only || c->B != 1)))
     return set_error("decoder_forward: peer output needs new_only, one scene and 1..%d peers", M3R_MAX_PEERS);
+  if (c->mem_mode < M3R_MEM_KV || c->mem_mode > M3R_MEM_RAW) return set_error("decoder_forward: bad mem_mode %d", c->mem_mode);
+  if (c->n_peers > 0 && c->mem_mode != M3R_MEM_KV) return set_error("decoder_forward: peer output needs mem_mode kv");
   DecWs ws;
   const int64_t need = dec_layout(w, c, workspace, workspace_bytes, &ws);
   if (need > workspace_bytes) return set_error("decoder_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
@@ -200,6 +210,8 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   const int D = w->embed_dim, Hh = w->num_heads, bf = w->is_bf16, B = c->B, G = c->G, Nm = c->Nm;
   const int M = (int)ws.M;
   const int Nt = (int)ws.Nt;
+  const int mode = c->mem_mode;
+  const int mw = mode == M3R_MEM_KV ? 2 * D : D;         // width of a memory row (decoder.py:189,277)
   int n_total = 0;
   for (int g = 0; g < G; ++g) n_total += c->groups[g].n_views;
   // make_mem_mask rule (decoder.py:199-204, 291-296): skip own tokens unless rendering or a lone first image
@@ -214,8 +226,8 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     for (int l = 0; l < w->depth; ++l) {
       if (!c->mem_out[l]) return set_error("decoder_forward: mem_out[%d] is null", l);
       if (c->mem[l] == c->mem_out[l]) continue;
-      cudaError_t e = cudaMemcpy2DAsync(c->mem_out[l], (size_t)c->mem_out_bstride_rows * 2 * D * 2, c->mem[l],
-                                        (size_t)c->mem_bstride_rows * 2 * D * 2, (size_t)Nm * 2 * D * 2, B,
+      cudaError_t e = cudaMemcpy2DAsync(c->mem_out[l], (size_t)c->mem_out_bstride_rows * mw * 2, c->mem[l],
+                                        (size_t)c->mem_bstride_rows * mw * 2, (size_t)Nm * mw * 2, B,
                                         cudaMemcpyDeviceToDevice, cps);
       if (e != cudaSuccess) return set_error("decoder_forward: memory copy failed: %s", cudaGetErrorString(e));
     }
@@ -261,6 +273,21 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     } else {
       xout = ws.x;
     }
+    if (mode != M3R_MEM_KV && Nm > 0) {
+      // memory_mode norm_y / raw: K|V of the stored rows are projected at use (layers.py:92-96); independent of x, so in
+      // update mode it shares the side stream with the new tokens' projection
+      void* mst = (side && !c->render) ? (void*)g_side.s : stream;
+      for (int bm = 0; bm < ws.nbm; ++bm) {
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(c->mem[l]) + (int64_t)bm * c->mem_bstride_rows * D;
+        if (mode == M3R_MEM_RAW) {
+          uint16_t* ln = ws.memln + (int64_t)bm * Nm * D;
+          M3R_TRY(m3r_layernorm16(src, D, b.normy_w, b.normy_b, w->ln_eps, Nm, D, ln, D, bf, mst));
+          src = ln;
+        }
+        M3R_TRY(gemm(src, D, b.kv_w, D, Nm, 2 * D, D, bf, b.kv_b, 0, nullptr, 0, ws.kvmem + (int64_t)bm * Nm * 2 * D, 2 * D,
+                     M3R_OUT_16, mst));
+      }
+    }
     // ---- self-attention (layers.py:91)
     M3R_TRY(m3r_layernorm(xin, D, nullptr, 0, b.norm1_w, b.norm1_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
     M3R_TRY(gemm(ws.h16, D, b.qkv_w, D, M, 3 * D, D, bf, b.qkv_b, 0, nullptr, 0, ws.qkv16, 3 * D, M3R_OUT_16, stream,
@@ -288,7 +315,11 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
       at.Q = ws.q16 + ws.row0[g] * D; at.ldq = D;
       const uint16_t* mem_l = Nm > 0 ? reinterpret_cast<const uint16_t*>(c->mem[l]) : nullptr;
       if (Nm > 0) {
-        at.K0 = mem_l; at.V0 = mem_l + D; at.ldk0 = 2 * D; at.kv_bstride0 = c->mem_bstride_rows; at.Nk0 = Nm;
+        if (mode == M3R_MEM_KV) {
+          at.K0 = mem_l; at.V0 = mem_l + D; at.ldk0 = 2 * D; at.kv_bstride0 = c->mem_bstride_rows; at.Nk0 = Nm;
+        } else {
+          at.K0 = ws.kvmem; at.V0 = ws.kvmem + D; at.ldk0 = 2 * D; at.kv_bstride0 = ws.nbm > 1 ? Nm : 0; at.Nk0 = Nm;
+        }
         if (!c->render) { at.K1 = ws.kvnew; at.V1 = ws.kvnew + D; at.ldk1 = 2 * D; at.kv_bstride1 = Nt; at.Nk1 = Nt; }
       } else {
         at.K0 = ws.kvnew; at.V0 = ws.kvnew + D; at.ldk0 = 2 * D; at.kv_bstride0 = Nt; at.Nk0 = Nt;   // first call: only new tokens
@@ -328,6 +359,24 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
       uint16_t* mo = reinterpret_cast<uint16_t*>(c->mem_out[l]);
       if (!mo) return set_error("decoder_forward: mem_out[%d] is null", l);
       const float* add = (off && l < w->depth - 1) ? off : nullptr;        // the last level gets no offset
+      if (mode != M3R_MEM_KV) {
+        // norm_y stores LN_y(new_mem + off), raw stores new_mem + off (layers.py:81-86), D-wide rows
+        for (int g = 0; g < G; ++g) {
+          const m3r_dec_group& gr = c->groups[g];
+          const int rows = gr.n_views * gr.N;
+          for (int bb = 0; bb < B; ++bb) {
+            const int64_t in_row = ws.row0[g] + (int64_t)bb * rows;
+            const float* xs = ws.snap + ((int64_t)l * M + in_row) * D;
+            const float* as = add ? add + in_row * D : nullptr;
+            uint16_t* dst = mo + ((int64_t)bb * c->mem_out_bstride_rows + (c->new_only ? 0 : Nm) + ws.tok0[g]) * D;
+            if (mode == M3R_MEM_NORM_Y)
+              M3R_TRY(m3r_layernorm(xs, D, as, D, b.normy_w, b.normy_b, w->ln_eps, rows, D, dst, D, M3R_OUT_16, bf, st));
+            else
+              M3R_TRY(m3r_add_cast16(xs, D, as, D, rows, D, dst, D, bf, st));
+          }
+        }
+        continue;
+      }
       M3R_TRY(m3r_layernorm(ws.snap + (int64_t)l * M * D, D, add, D, b.normy_w, b.normy_b, w->ln_eps, M, D, hbuf, D, M3R_OUT_16, bf, st));
       for (int g = 0; g < G; ++g) {
         const m3r_dec_group& gr = c->groups[g];

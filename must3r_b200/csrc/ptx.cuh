@@ -256,5 +256,13 @@ __device__ __forceinline__ uint32_t pack16(float lo, float hi, int is_bf16) {
   }
   return r;
 }
+__device__ __forceinline__ float unpack16_lo(uint32_t w, int is_bf16) {
+  if (is_bf16) return __uint_as_float(w << 16);
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(w & 0xffffu)));
+}
+__device__ __forceinline__ float unpack16_hi(uint32_t w, int is_bf16) {
+  if (is_bf16) return __uint_as_float(w & 0xffff0000u);
+  return __half2float(__ushort_as_half(static_cast<unsigned short>(w >> 16)));
+}
 
 }  // namespace m3r

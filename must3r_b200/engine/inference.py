@@ -21,17 +21,31 @@ from ..model.common import ActivationType
 
 
 # --------------------------------------------------------------------------------------------- host copies
-_PENDING_HOST_COPIES = [False]
+_PENDING_HOST_COPIES = []       # read-back streams with device->host copies not yet waited for
+_D2H_STREAMS = {}               # device index -> side stream used only for result read-back
+
+
+def _d2h_stream(device):
+    st = _D2H_STREAMS.get(device.index)
+    if st is None:
+        st = _D2H_STREAMS[device.index] = torch.cuda.Stream(device=device)
+    return st
 
 
 def _to_out(v, outdevice):
     """`.to(outdevice)` of the reference (engine/inference.py:196), except that device->host results go through pinned
-    staging buffers with an asynchronous copy, so the D2H traffic overlaps the next decoder steps instead of stalling
-    the launch thread.  `_sync_host_copies()` is called before results are handed to any callback or returned."""
+    staging buffers and an asynchronous copy on a dedicated read-back stream, so the D2H traffic overlaps the next
+    decoder steps instead of stalling the launch thread or the compute stream.  `_sync_host_copies()` is called before
+    results are handed to any callback or returned."""
     if v.is_cuda and str(outdevice) == "cpu":
         dst = torch.empty(v.shape, dtype=v.dtype, pin_memory=True)
-        dst.copy_(v, non_blocking=True)
-        _PENDING_HOST_COPIES[0] = True
+        cur = torch.cuda.current_stream(v.device)
+        st = _d2h_stream(v.device)
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            dst.copy_(v, non_blocking=True)
+        v.record_stream(st)
+        _PENDING_HOST_COPIES.append(st)
         return dst
     return v.to(outdevice)
 
@@ -54,9 +68,10 @@ def _with_host_shape(true_shape_group, device):
 
 
 def _sync_host_copies():
-    if _PENDING_HOST_COPIES[0]:
-        torch.cuda.current_stream().synchronize()
-        _PENDING_HOST_COPIES[0] = False
+    if _PENDING_HOST_COPIES:
+        for st in set(_PENDING_HOST_COPIES):
+            st.synchronize()
+        _PENDING_HOST_COPIES.clear()
 
 
 # --------------------------------------------------------------------------------------------- postprocess

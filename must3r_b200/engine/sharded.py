@@ -31,6 +31,8 @@ from typing import Callable, List, Optional
 import torch
 import torch.distributed as dist
 
+from .inference import _sync_host_copies, _to_out
+
 _LIVE_ARENAS = []      # arenas backing memory tuples handed back to callers (return_mem=True)
 _ARENA_CACHE = {}      # (nbytes, device) -> PeerArena reused by calls that do not hand their memory back
 
@@ -120,6 +122,7 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
 
     n_init = min(2, V)
     fused = (world > 1 and x.is_cuda and hasattr(decoder, "update_tokens_to_peers")
+             and getattr(decoder, "memory_mode", "kv") == "kv"      # the GEMM epilogue that stores to peers is the K|V one
              and os.environ.get("M3R_FUSED_GATHER", "1") != "0")
     arena = None
     if fused:
@@ -204,11 +207,12 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
         pm = pm[0]
         if post_process_function is not None:
             res = post_process_function(pm)
-            res = {k: (v.cpu() if to_host else v) for k, v in res.items()}
+            res = {k: (_to_out(v, "cpu") if to_host else v) for k, v in res.items()}
             outs.extend({k: v[j] for k, v in res.items()} for j in range(pm.shape[0]))
         else:
-            pm = pm.cpu() if to_host else pm
+            pm = _to_out(pm, "cpu") if to_host else pm
             outs.extend(pm[j] for j in range(pm.shape[0]))
+    _sync_host_copies()
     if arena is not None and return_mem:
         _LIVE_ARENAS.append(arena)           # the returned memory tensors are views of the arena
     return (mem, outs) if return_mem else outs

@@ -53,7 +53,11 @@ class DecoderCall(C.Structure):
     _fields_ = [("B", C.c_int32), ("G", C.c_int32), ("groups", C.POINTER(DecGroup)), ("Nm", C.c_int32),
                 ("mem", C.POINTER(C.c_void_p)), ("mem_bstride_rows", C.c_int64), ("render", C.c_int32),
                 ("is_init", C.c_int32), ("mem_out", C.POINTER(C.c_void_p)), ("mem_out_bstride_rows", C.c_int64),
-                ("new_only", C.c_int32), ("n_peers", C.c_int32), ("peer_mem", C.POINTER(C.c_void_p))]
+                ("new_only", C.c_int32), ("n_peers", C.c_int32), ("peer_mem", C.POINTER(C.c_void_p)),
+                ("mem_mode", C.c_int32)]
+
+
+MEM_MODE_CODE = {"kv": 0, "norm_y": 1, "raw": 2}        # M3R_MEM_* (must3r/model/blocks/layers.py:9)
 
 
 _lib.SIGNATURES.update({

@@ -199,9 +199,6 @@ class MUSt3R(nn.Module):
     def forward_list(self, x, pos, true_shape, current_mem=None, render=False, return_feats=False, _new_only=False,
                      _peer_ptrs=None):
         """decoder.py:158-265"""
-        if self.memory_mode != 'kv':
-            raise NotImplementedError("must3r_b200 implements memory_mode='kv' (the released checkpoints' mode); "
-                                      f"got {self.memory_mode!r}")
         if not x[0].is_cuda:
             raise RuntimeError("must3r_b200.MUSt3R runs on CUDA only (no CPU fallback)")
         dev = x[0].device
@@ -209,6 +206,9 @@ class MUSt3R(nn.Module):
         w = self._packed(dtype)
         lib = _lib.lib()
         D, G = self.embed_dim, len(x)
+        mem_D = 2 * D if self.memory_mode == "kv" else D                  # decoder.py:189,277
+        if _peer_ptrs and self.memory_mode != "kv":
+            raise RuntimeError("peer output (fused gather) needs memory_mode='kv'")
         B = x[0].shape[0]
         groups = (cm.DecGroup * G)()
         keep, outs = [], []
@@ -242,6 +242,7 @@ class MUSt3R(nn.Module):
         call.B, call.G, call.groups = B, G, groups
         call.render = 1 if render else 0
         call.is_init = 1 if current_mem is None else 0
+        call.mem_mode = cm.MEM_MODE_CODE[self.memory_mode]
         if current_mem is None:
             mem_vals, labels, mem_nimgs, mem_pi, mem_pt = None, torch.zeros((B, 0), dtype=torch.int64, device=dev), 0, 0, 0
             Nm = 0
@@ -254,13 +255,14 @@ class MUSt3R(nn.Module):
             mv = []
             for l in range(self.depth):
                 m = mem_vals[l]
-                assert m.shape[0] == B and m.shape[2] == 2 * D
-                if m.dtype != dtype or m.stride(2) != 1 or m.stride(1) != 2 * D:
+                assert m.shape[0] == B and m.shape[2] == mem_D, \
+                    f"memory rows are {m.shape[2]} wide, memory_mode={self.memory_mode!r} expects {mem_D}"
+                if m.dtype != dtype or m.stride(2) != 1 or m.stride(1) != mem_D:
                     m = m.to(dtype).contiguous()
                 mv.append(m)
                 mem_ptrs[l] = m.data_ptr()
             keep.append(mv)
-            bstrides = {m.stride(0) // (2 * D) if B > 1 else Nm for m in mv}
+            bstrides = {m.stride(0) // mem_D if B > 1 else Nm for m in mv}
             assert len(bstrides) == 1
             call.mem = mem_ptrs
             call.mem_bstride_rows = bstrides.pop()
@@ -268,7 +270,7 @@ class MUSt3R(nn.Module):
         new_mem = None
         if not render:
             rows = Nt if _new_only else Nm + Nt
-            new_mem = [torch.empty((B, rows, 2 * D), dtype=dtype, device=dev) for _ in range(self.depth)]
+            new_mem = [torch.empty((B, rows, mem_D), dtype=dtype, device=dev) for _ in range(self.depth)]
             for l in range(self.depth):
                 out_ptrs[l] = new_mem[l].data_ptr()
             call.mem_out = out_ptrs

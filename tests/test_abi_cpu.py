@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.m3r_abi_version() == 2
+    assert lib.m3r_abi_version() == 3
 
 
 def test_ctypes_structs_match_the_c_layout(tmp_path):

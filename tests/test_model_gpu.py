@@ -45,6 +45,8 @@ VARIANTS = {
     "f0": (dict(pos_embed="RoPE100_224:512"), dict(pos_embed="RoPE100_224:512")),
     "nofb": ({}, dict(feedback_type=None)),
     "fblin": ({}, dict(feedback_type="single_linear")),
+    "normy": ({}, dict(memory_mode="norm_y")),          # memory rows = norm_y(x), K|V projected at use (layers.py:85,94)
+    "raw": ({}, dict(memory_mode="raw")),               # memory rows = x, norm_y + projection at use (layers.py:82,92)
 }
 
 
@@ -205,7 +207,39 @@ def test_no_cpu_fallback_and_arg_errors():
         enc(imgs, ts)
     with pytest.raises(AssertionError):
         enc(torch.zeros(1, 3, 40, 48, device="cuda"), ts.cuda())
-    dec.change_memory_mode("norm_y")
     x, pos = enc(imgs.cuda(), ts.cuda())
+    mem, _ = dec(x[None], pos[None], ts.cuda()[None], None)
+    dec.change_memory_mode("norm_y")                      # a K|V memory handed to a norm_y decoder is a width error
+    with pytest.raises(AssertionError, match="memory_mode"):
+        dec(x[None], pos[None], ts.cuda()[None], mem)
     with pytest.raises(NotImplementedError):
-        dec(x[None], pos[None], ts.cuda()[None], None)
+        dec(x[None], pos[None], ts.cuda()[None], None, return_feats=True)
+
+
+@pytest.mark.parametrize("mode", ["norm_y", "raw"])
+def test_memory_modes_match_kv(mode):
+    """the three memory modes give the same pointmaps (bit-identical in the fp32 reference; here the stored
+    rows are rounded to 16 bit at a different point, so equal within the 16-bit tolerance), incl. batch 2 and an expanded
+    (stride-0) memory at render time (engine/inference.py:668-683)."""
+    set_precision(torch.float16)
+    enc, dec = tiny_cuda(7)
+    imgs, ts = syn.synthetic_views(6, 32, 48, seed=12)
+    x, pos = enc(imgs.cuda(), ts.cuda())
+    ts = ts.cuda()
+    xb, pb, tb = x.view(2, 3, *x.shape[1:]), pos.view(2, 3, *pos.shape[1:]), ts.view(2, 3, 2)
+
+    def chain(m):
+        dec.change_memory_mode(m)
+        mem, pm0 = dec(xb[:, :2], pb[:, :2], tb[:, :2], None)
+        mem, pm1 = dec(xb[:, 2:3], pb[:, 2:3], tb[:, 2:3], mem)
+        _, pm2 = dec(xb, pb, tb, mem, render=True)
+        one = ([v[:1].expand(3, -1, -1) for v in mem[0]], mem[1][:1].expand(3, -1), *mem[2:])
+        _, pm3 = dec(xb[0][:, None], pb[0][:, None], tb[0][:, None], one, render=True)     # 3 "scenes" sharing one memory
+        return mem, [pm0, pm1, pm2, pm3]
+
+    mem_kv, ref = chain("kv")
+    mem_m, got = chain(mode)
+    assert mem_m[0][0].shape[2] == dec.embed_dim and mem_kv[0][0].shape[2] == 2 * dec.embed_dim
+    for a, b in zip(got, ref):
+        assert rel(a.cpu(), b.cpu()) < TOL[torch.float16]
+    assert rel(got[3].cpu()[:, 0], got[2].cpu()[0]) < TOL[torch.float16]

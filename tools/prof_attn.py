@@ -44,6 +44,13 @@ if "attn" in which:
         ms = timeit(fn)
         fl = 4.0 * B * H * Nq * Nk * 64
         print(f"attn {name:28s} {ms*1e3:9.1f} us  {fl/ms/1e9 if ms else 0:8.1f} TFLOP/s", flush=True)
+if "upd" in which:           # the one-view update cross-attention alone (ncu target)
+    B, H, Nq, Nk = 1, 12, 768, 7680
+    D = H * 64
+    q = torch.randn(B * Nq, D, device="cuda").to(dt)
+    kv = torch.randn(B * Nk, 2 * D, device="cuda").to(dt)
+    ms = timeit(lambda: ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk))
+    print(f"attn update CA 1 view x M=10 {ms*1e3:9.1f} us  {4.0*B*H*Nq*Nk*64/ms/1e9 if ms else 0:8.1f} TFLOP/s", flush=True)
 if "gemm" in which:
     for name, (M, N, K) in {
         "enc qkv 20v": (15360, 3072, 1024), "enc proj 20v": (15360, 1024, 1024), "enc fc1 20v": (15360, 4096, 1024),
