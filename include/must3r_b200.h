@@ -44,9 +44,10 @@ long long m3r_launch_count(void);
  * other (28 doubles). */
 void m3r_prof_enable(int on);
 int m3r_prof_read(double* out);
-/* Debug hook (tools/trace_attn.py): device buffer of 64 x #CTAs uint64 that subsequent m3r_attention launches fill with
- * %globaltimer stamps of one softmax thread per CTA (entry, per-tile barrier waits, epilogue, merge); NULL = off. */
-int m3r_debug_attn_trace(void* buf);
+/* Debug hook (tools/trace_attn.py, tools/trace_gemm.py): device buffer that subsequent attention / GEMM launches fill
+ * with %globaltimer stamps (64 / 16 uint64 per CTA: entry, barrier waits, epilogue, exit); NULL = off.  Only builds made
+ * with M3R_TRACE=1 carry the stamps; otherwise the call fails with an error. */
+int m3r_debug_trace(void* buf);
 
 /* ---------------------------------------------------------------------------------------------------
  * Linear layer y = act(x W^T + b) (+ residual) on tcgen05 tensor cores.

@@ -50,7 +50,7 @@ class AttnArgs(C.Structure):
 SIGNATURES = {
     "m3r_last_error": (C.c_char_p, []),
     "m3r_abi_version": (C.c_int, []),
-    "m3r_debug_attn_trace": (C.c_int, [C.c_void_p]),
+    "m3r_debug_trace": (C.c_int, [C.c_void_p]),
     "m3r_launch_count": (C.c_longlong, []),
     "m3r_prof_enable": (None, [C.c_int]),
     "m3r_prof_read": (C.c_int, [C.POINTER(C.c_double)]),

@@ -34,14 +34,17 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math_off_placeholder"]
-    if os.environ.get("M3R_ATTN_TRACE") == "1":          # debug build: in-kernel %globaltimer stamps (tools/trace_attn.py)
-        flags.append("-DM3R_ATTN_TRACE")
-        force = True
+    variant = "trace" if os.environ.get("M3R_TRACE") == "1" else "release"
+    if variant == "trace":                               # debug build: in-kernel %globaltimer stamps (tools/trace_*.py)
+        flags.append("-DM3R_TRACE")
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     headers.append(os.path.join(os.path.dirname(HERE), "include", "must3r_b200.h"))
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
+    marker = os.path.join(objdir, ".variant")
+    if not os.path.exists(marker) or open(marker).read().strip() != variant:
+        force = True                                     # objects of the other variant must not be linked in
     nvcc = _nvcc()
 
     def compile_one(src):
@@ -64,6 +67,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(marker, "w") as f:
+        f.write(variant)
     return OUT
 
 

@@ -55,11 +55,9 @@ struct AttnParams {
   int* split_cnt;            // [B, H, ceil(Nq/128)] arrival counters (zero on entry, reset by the last arriver)
   int H;
   long long rows_total;      // B * Nq
-  unsigned long long* trace; // debug only (m3r_debug_attn_trace): per-CTA clock stamps, 64 words per CTA; normally null
+  unsigned long long* trace; // debug only (m3r_debug_trace): per-CTA clock stamps, 64 words per CTA; normally null
 };
 
-__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 
 struct TileIt {
   int seg, t;          // current tile
@@ -183,12 +181,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* o_done = p_full + 2;       // [2] MMA -> softmax x : P_x(j) V(j) accumulated into O_x, P columns free again
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
-#ifdef M3R_ATTN_TRACE
-  const unsigned long long t_entry = p.trace ? gtime_ns() : 0ull;
-#define M3R_TR(...) __VA_ARGS__
-#else
-#define M3R_TR(...)
-#endif
+  M3R_TR(const unsigned long long t_entry = p.trace ? gtime_ns() : 0ull;)
   const int warp = threadIdx.x >> 5;
   const int qblk = blockIdx.x, h = blockIdx.y;
   const int b = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
@@ -552,20 +545,6 @@ static size_t g_split_cap = 0;
 }  // namespace m3r
 
 // Number of fp32 scratch elements m3r_attention may need for a problem (0 if it will not split).
-static unsigned long long* g_attn_trace = nullptr;
-// Debug hook (tools/trace_attn.py): device buffer of 64 x #CTAs uint64 that the next m3r_attention launches fill with
-// %globaltimer stamps of softmax warp 0 (entry, per-tile barrier waits, epilogue, merge); nullptr switches it off.
-// Compiled in only with -DM3R_ATTN_TRACE (M3R_ATTN_TRACE=1 python -m must3r_b200.build): the stamps cost registers.
-extern "C" int m3r_debug_attn_trace(void* buf) {
-#ifdef M3R_ATTN_TRACE
-  g_attn_trace = reinterpret_cast<unsigned long long*>(buf);
-  return 0;
-#else
-  (void)buf;
-  return m3r::set_error("attention trace not compiled in (build with M3R_ATTN_TRACE=1)");
-#endif
-}
-
 extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   using namespace m3r;
   if (!a || !a->Q || !a->K0 || !a->V0 || !a->O) return set_error("attention: null pointer");
@@ -599,7 +578,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   // ---- shape heuristics (tools/prof_attn.py sweep, profiles/r01_attention_sweep.txt):
   //  * enough work for ~half a wave of 2-tile CTAs -> QT=2 (K/V tiles shared by two query tiles, ping-pong), no split;
   //  * otherwise (one view per step) QT=1, two CTAs per SM, and the key range split so that ~2 CTAs per SM exist,
-  //    keeping at least 3 key tiles per split; a combine kernel merges the partial results.
+  //    keeping at least 4 key tiles per split; the last CTA of a (batch, head, tile) to finish merges the partials.
   const int sms = num_sms();
   const int key_tiles = (a->Nk0 + AT_BN - 1) / AT_BN + (a->Nk1 + AT_BN - 1) / AT_BN;   // upper bound
   const int ctas2 = ((a->Nq + 255) / 256) * a->H * a->B;
@@ -609,7 +588,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   int splits = 1;
   if (qt == 1 && ctas1 < 2 * sms) {
     splits = (2 * sms + ctas1 / 2) / ctas1;
-    if (splits > key_tiles / 3) splits = key_tiles / 3;
+    if (splits > key_tiles / 4) splits = key_tiles / 4;        // a split pays ~2 us of partial store + merge: >= 4 tiles each
   }
   if (const char* f = getenv("M3R_ATTN_SPLITS")) { const int v = atoi(f); if (v >= 1) splits = v; }
   if (splits > key_tiles) splits = key_tiles;
@@ -623,7 +602,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   p.splits = splits; p.sl2 = a->scale * 1.4426950408889634f;
   p.O = a->O; p.ldo = a->ldo; p.H = a->H; p.rows_total = (long long)a->B * a->Nq;
   p.part_o = nullptr; p.part_ml = nullptr; p.split_cnt = nullptr;
-  p.trace = g_attn_trace;
+  p.trace = trace_buffer();
   if (splits > 1) {
     // scratch layout: [4096 arrival counters | partial O | partial (m, l)].  The counters sit at a fixed place, are
     // zeroed once when the buffer is (re)allocated and every launch leaves them zero again (last arriver resets).

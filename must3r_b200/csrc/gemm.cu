@@ -43,6 +43,7 @@ struct GemmParams {
   long long batch_stride_rows;
   int n_peer_out;
   void* peer_out[M3R_MAX_PEERS];
+  unsigned long long* trace;   // debug only (m3r_debug_trace): 16 words per CTA; normally null
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -135,6 +136,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
+  M3R_TR(unsigned long long* tr = p.trace ? p.trace + 16ull * blockIdx.x : nullptr;
+         if (tr && threadIdx.x == 0) { tr[0] = gtime_ns(); tr[8] = smid(); })
   const int warp = threadIdx.x >> 5;
   const int tiles_m = (p.M + BM - 1) / BM;
   const int tiles_n = p.N / BN;
@@ -156,8 +159,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  M3R_TR(if (tr && threadIdx.x == 0) tr[1] = gtime_ns();)
   griddep_wait();        // everything above overlapped the previous kernel's tail
   griddep_launch();
+  M3R_TR(if (tr && threadIdx.x == 0) tr[2] = gtime_ns();)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -174,6 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      M3R_TR(if (tr) tr[3] = gtime_ns();)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -186,6 +192,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
+        M3R_TR(if (tr && kb == 0 && t == (int)blockIdx.x && (threadIdx.x & 31) == 0) tr[4] = gtime_ns();)
         tc_fence_after();
         if (elect_one()) {
           const uint64_t adesc = smem_desc_sw128(smem_u32(sA + stage * BM * BK * 2));
@@ -197,6 +204,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           umma_commit(&empty[stage]);                       // frees the smem stage when the MMAs retire
           if (kb == num_kb - 1) umma_commit(&tfull[as]);    // accumulator complete
+          M3R_TR(if (tr && kb == num_kb - 1) tr[5] = gtime_ns();)
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -220,6 +228,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const float* rope_row = p.rope_tab ? p.rope_tab + (long long)(row % p.rope_period) * 64 : nullptr;
 
       mbar_wait(&tfull[as], aphase);
+      M3R_TR(if (tr && threadIdx.x == 64) tr[6] = gtime_ns();)
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
@@ -233,12 +242,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
         epilogue_chunk(p, raw, row, row_ok, orow, rb_on, rope_row, n0 + c * 32);
       }
+      M3R_TR(if (tr && threadIdx.x == 64) tr[7] = gtime_ns();)
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  M3R_TR(if (tr && threadIdx.x == 0) tr[9] = gtime_ns();)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -259,6 +270,7 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream) {
   p.out = a->out; p.ldc = a->ldc; p.out_dtype = a->out_dtype;
   p.rows_per_batch = a->rows_per_batch; p.batch_stride_rows = a->batch_stride_rows;
   p.n_peer_out = a->n_peer_out;
+  p.trace = trace_buffer();
   for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
@@ -428,6 +440,7 @@ static int launch_gemm_pair(const m3r_gemm_args* a, cudaStream_t stream) {
   p.out = a->out; p.ldc = a->ldc; p.out_dtype = a->out_dtype;
   p.rows_per_batch = a->rows_per_batch; p.batch_stride_rows = a->batch_stride_rows;
   p.n_peer_out = a->n_peer_out;
+  p.trace = trace_buffer();
   for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
   static bool attr_set = false;
   if (!attr_set) {

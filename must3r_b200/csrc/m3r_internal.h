@@ -32,6 +32,7 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int is_bf16, uint64_t cols,
 
 // Launch with the programmatic-stream-serialization attribute (PDL); M3R_PDL=0 in the environment disables it.
 bool pdl_enabled();
+unsigned long long* trace_buffer();            // device buffer set by m3r_debug_trace (nullptr = off)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

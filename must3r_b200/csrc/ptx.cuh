@@ -245,6 +245,15 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       : "memory");
 }
 
+// ------------------------------------------------------------------ debug timeline (builds with -DM3R_TRACE only)
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t) :: "memory"); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+#ifdef M3R_TRACE
+#define M3R_TR(...) __VA_ARGS__
+#else
+#define M3R_TR(...)
+#endif
+
 // ------------------------------------------------------------------ 16-bit packing
 // is_bf16 selects the storage format of the 16-bit operands at run time (both run at the same MMA rate).
 __device__ __forceinline__ uint32_t pack16(float lo, float hi, int is_bf16) {

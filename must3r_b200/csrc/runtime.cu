@@ -19,6 +19,9 @@ int set_error(const char* fmt, ...) {
   return 1;
 }
 
+static unsigned long long* g_trace = nullptr;
+unsigned long long* trace_buffer() { return g_trace; }
+
 bool pdl_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("M3R_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -159,4 +162,17 @@ extern "C" int m3r_ipc_open(const void* handle64, void** ptr) {
 extern "C" int m3r_ipc_close(void* ptr) {
   cudaError_t e = cudaIpcCloseMemHandle(ptr);
   return e == cudaSuccess ? 0 : m3r::set_error("ipc_close: %s", cudaGetErrorString(e));
+}
+
+// Debug hook (tools/trace_attn.py, tools/trace_gemm.py): device buffer that the next attention / GEMM launches fill with
+// %globaltimer stamps (64 / 16 uint64 per CTA); nullptr switches it off.  The stamps are compiled in only with -DM3R_TRACE
+// (M3R_TRACE=1 python -m must3r_b200.build): they cost registers in the hot loops.
+extern "C" int m3r_debug_trace(void* buf) {
+#ifdef M3R_TRACE
+  m3r::g_trace = reinterpret_cast<unsigned long long*>(buf);
+  return 0;
+#else
+  (void)buf;
+  return m3r::set_error("kernel trace not compiled in (build with M3R_TRACE=1)");
+#endif
 }

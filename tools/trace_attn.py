@@ -1,4 +1,4 @@
-"""Timeline of the attention kernel from inside (m3r_debug_attn_trace): where a launch's microseconds go.
+"""Timeline of the attention kernel from inside (m3r_debug_trace): where a launch's microseconds go.
 
     python tools/trace_attn.py [Nk=7680] [B=1] [qt] [splits]
 """
@@ -24,10 +24,10 @@ for cold in (True, False):
     if cold:
         flush.zero_()
     torch.cuda.synchronize()
-    lib.m3r_debug_attn_trace(buf.data_ptr())
+    lib.m3r_debug_trace(buf.data_ptr())
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); fn(); b.record(); torch.cuda.synchronize()
-    lib.m3r_debug_attn_trace(None)
+    lib.m3r_debug_trace(None)
     t = buf.view(-1, 64).cpu()
     t = t[t[:, 0] != 0]
     t0 = int(t[:, 0].min())
