@@ -84,6 +84,10 @@ typedef struct {
    * process with m3r_ipc_open (peer stores travel over NVLink while the kernel is still computing other tiles). */
   int32_t n_peer_out;
   void* peer_out[M3R_MAX_PEERS];
+  /* 1 = W is not written by the launch that precedes this one in the stream (model weights): the kernel then requests
+   * its first weight tiles before the programmatic-dependency wait, hiding their HBM latency behind the predecessor's
+   * tail.  0 = no assumption. */
+  int32_t w_static;
 } m3r_gemm_args;
 
 int m3r_gemm(const m3r_gemm_args* args, void* stream);

@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("batch_stride_rows", C.c_int64),
         ("n_peer_out", C.c_int32),
         ("peer_out", C.c_void_p * 8),
+        ("w_static", C.c_int32),
     ]
 
 

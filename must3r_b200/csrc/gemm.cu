@@ -44,6 +44,7 @@ struct GemmParams {
   int n_peer_out;
   void* peer_out[M3R_MAX_PEERS];
   unsigned long long* trace;   // debug only (m3r_debug_trace): 16 words per CTA; normally null
+  int w_static;                // weights may be requested before the programmatic-dependency wait
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -160,28 +161,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   M3R_TR(if (tr && threadIdx.x == 0) tr[1] = gtime_ns();)
-  griddep_wait();        // everything above overlapped the previous kernel's tail
-  griddep_launch();
-  M3R_TR(if (tr && threadIdx.x == 0) tr[2] = gtime_ns();)
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
+      // The weights never depend on the kernel before this one, so the W halves of the first ring of stages are requested
+      // BEFORE the programmatic-dependency wait: their (cold, HBM) latency overlaps the predecessor's tail.  The
+      // activations follow after the wait; each stage's barrier expects both halves.
+      int pre = 0;
+      if (p.w_static && blockIdx.x < num_tiles) {
+        const int n0 = (blockIdx.x / tiles_m) * BN;
+        pre = num_kb < STAGES ? num_kb : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {
+          mbar_arrive_expect_tx(&full[kb], Cfg::STAGE_BYTES);
+          tma_load_2d(sB + kb * BN * BK * 2, &tmW, &full[kb], kb * BK, n0);
+        }
+      }
+      griddep_wait();
+      griddep_launch();
+      M3R_TR(if (tr) tr[2] = gtime_ns();)
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t % tiles_m) * BM;
         const int n0 = (t / tiles_m) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-          tma_load_2d(sA + stage * BM * BK * 2, &tmA, &full[stage], kb * BK, m0);
-          tma_load_2d(sB + stage * BN * BK * 2, &tmW, &full[stage], kb * BK, n0);
+          if (pre > 0) {                      // stage already armed, W half in flight
+            --pre;
+            tma_load_2d(sA + stage * BM * BK * 2, &tmA, &full[stage], kb * BK, m0);
+          } else {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+            tma_load_2d(sA + stage * BM * BK * 2, &tmA, &full[stage], kb * BK, m0);
+            tma_load_2d(sB + stage * BN * BK * 2, &tmW, &full[stage], kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
       M3R_TR(if (tr) tr[3] = gtime_ns();)
+    } else {
+      griddep_wait();
+      griddep_launch();
     }
   } else if (warp == 1) {
+    griddep_wait();        // everything above overlapped the previous kernel's tail
+    griddep_launch();
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc(BM, BN, p.is_bf16 ? 1u : 0u, 0, 0);
     int stage = 0; uint32_t phase = 0;
@@ -213,6 +236,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (2..9)
+    griddep_wait();
+    griddep_launch();
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
     const int chalf = (warp - 2) >> 2;            // which half of the tile's columns this warp drains
     const int lane = threadIdx.x & 31;
@@ -271,6 +296,7 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream) {
   p.rows_per_batch = a->rows_per_batch; p.batch_stride_rows = a->batch_stride_rows;
   p.n_peer_out = a->n_peer_out;
   p.trace = trace_buffer();
+  p.w_static = a->w_static;
   for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
   static bool attr_set = false;
   if (!attr_set) {
@@ -441,6 +467,7 @@ static int launch_gemm_pair(const m3r_gemm_args* a, cudaStream_t stream) {
   p.rows_per_batch = a->rows_per_batch; p.batch_stride_rows = a->batch_stride_rows;
   p.n_peer_out = a->n_peer_out;
   p.trace = trace_buffer();
+  p.w_static = a->w_static;
   for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
   static bool attr_set = false;
   if (!attr_set) {

@@ -35,6 +35,7 @@ static int gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, i
                 int64_t batch_stride_rows = 0, int n_peer_out = 0, void* const* peer_out = nullptr) {
   m3r_gemm_args a;
   a.n_peer_out = n_peer_out;
+  a.w_static = 1;                  // every GEMM of the model multiplies by checkpoint weights
   for (int i = 0; i < M3R_MAX_PEERS; ++i) a.peer_out[i] = i < n_peer_out ? peer_out[i] : nullptr;
   a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.M = M; a.N = N; a.K = K; a.is_bf16 = is_bf16;
   a.bias = bias; a.act = act; a.residual = residual; a.ldr = ldr;

@@ -34,9 +34,10 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rb_period: int = 1,
            rb_first: int = 0, rope_tab: Optional[torch.Tensor] = None, rope_cols: int = 0,
            out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
-           rows_per_batch: int = 0, batch_stride_rows: int = 0, peer_ptrs=()) -> torch.Tensor:
+           rows_per_batch: int = 0, batch_stride_rows: int = 0, peer_ptrs=(), w_static: bool = False) -> torch.Tensor:
     """out = act(a @ w.T + bias [+rope]) [+ residual]; a [M,K] and w [N,K] fp16/bf16, fp32 accumulate.
-    peer_ptrs: device pointers (ints) that receive a copy of the 16-bit output (fused GEMM -> all-gather)."""
+    peer_ptrs: device pointers (ints) that receive a copy of the 16-bit output (fused GEMM -> all-gather).
+    w_static: w is a weight that the previous launch on this stream does not write (lets the kernel fetch it early)."""
     _req_cuda(a, w)
     assert a.dtype in F16 and w.dtype == a.dtype and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1
@@ -67,6 +68,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if out.dtype != torch.float32:
         assert out.dtype == a.dtype
     args.rows_per_batch, args.batch_stride_rows = rows_per_batch, batch_stride_rows
+    args.w_static = 1 if w_static else 0
     args.n_peer_out = len(peer_ptrs)
     for i, ptr in enumerate(peer_ptrs):
         args.peer_out[i] = ptr

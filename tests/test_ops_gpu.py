@@ -38,6 +38,33 @@ def test_gemm_plain(dtype, bn, M, N, K):
         os.environ.pop("M3R_GEMM_BN", None)
 
 
+@pytest.mark.parametrize("M,N,K", [(768, 768, 768), (200, 256, 128), (5000, 1024, 1024), (768, 768, 3072)])
+def test_gemm_static_weight_prefetch(M, N, K):
+    """w_static=True: the weight halves of the first ring of stages are requested before the programmatic-dependency wait
+    (K shorter / longer than the ring, more tiles than SMs); results must not change, also back to back on one stream."""
+    dtype = torch.float16
+    a, w = rnd(M, K, dtype=dtype, seed=1), rnd(N, K, dtype=dtype, seed=2, scale=K ** -0.5)
+    bias = rnd(N, seed=3)
+    ref = ops.linear(a, w, bias, out_dtype=torch.float32)
+    for bn in (64, 128, 256):
+        os.environ["M3R_GEMM_BN"] = str(bn)
+        try:
+            outs = [ops.linear(a, w, bias, out_dtype=torch.float32, w_static=True) for _ in range(3)]
+        finally:
+            os.environ.pop("M3R_GEMM_BN", None)
+        for o in outs:
+            assert torch.equal(o, ref) or rel_l2(o, ref) < 1e-6
+    # a chain of dependent launches: each GEMM consumes the previous one's output as its activations
+    x = a
+    for _ in range(4):
+        x = ops.linear(x, w[:K] if N >= K else w, None, w_static=True) if N == K else x
+    if N == K:
+        y = a
+        for _ in range(4):
+            y = ops.linear(y, w, None)
+        assert torch.equal(x, y)
+
+
 @pytest.mark.parametrize("dtype", DT)
 def test_gemm_large_persistent(dtype):
     """More tiles than SMs: exercises the persistent loop, the smem ring wrap and the TMEM double buffer."""

@@ -61,7 +61,7 @@ if "gemm" in which:
     }.items():
         a = torch.randn(M, K, device="cuda").to(dt); w = torch.randn(N, K, device="cuda").to(dt)
         out = torch.empty(M, N, device="cuda", dtype=dt)
-        ms = timeit(lambda: ops.linear(a, w, None, out=out))
+        ms = timeit(lambda: ops.linear(a, w, None, out=out, w_static=True))
         print(f"gemm {name:14s} M={M:6d} N={N:5d} K={K:5d} {ms*1e3:9.1f} us  {2.0*M*N*K/ms/1e9 if ms else 0:8.1f} TFLOP/s", flush=True)
 
 if "sweep" in which:
@@ -92,7 +92,7 @@ if "small" in which:
         for bn in (64, 128, 256):
             if N % bn: continue
             _os.environ["M3R_GEMM_BN"] = str(bn)
-            res.append((timeit(lambda: ops.linear(a, w, None, out=out), iters=15), bn))
+            res.append((timeit(lambda: ops.linear(a, w, None, out=out, w_static=True), iters=15), bn))
         _os.environ.pop("M3R_GEMM_BN")
         print(f"small gemm {name:12s} M={M} N={N} K={K}: " + "  ".join(f"BN{b}:{m*1e3:.1f}us" for m, b in res), flush=True)
     x = torch.randn(768, 768, device="cuda"); g = torch.ones(768, device="cuda"); b = torch.zeros(768, device="cuda")

@@ -14,7 +14,7 @@ dt = torch.bfloat16
 a = torch.randn(M, K, device="cuda").to(dt); w = torch.randn(N, K, device="cuda").to(dt)
 bias = torch.randn(N, device="cuda"); res = torch.randn(M, N, device="cuda")
 out = torch.empty(M, N, device="cuda", dtype=torch.float32)
-fn = lambda: ops.linear(a, w, bias, residual=res, out=out)  # noqa: E731  (the proj / fc2 form: bias + fp32 residual, fp32 out)
+fn = lambda: ops.linear(a, w, bias, residual=res, out=out, w_static=True)  # noqa: E731  (the proj / fc2 form: bias + fp32 residual, fp32 out)
 fn(); fn()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 lib = _lib.lib()
