@@ -41,6 +41,16 @@ def flops_per_job(V, mem_views_schedule):
     return enc + upd + ren
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE representative launch of each kernel category, from the
+# `ncu --set full` captures summarised under profiles/ (bench.py cannot run ncu itself); `launch` names the shape.
+NCU_TRAFFIC = {
+    "gemm_kernel<64>": {"bytes": 4.76e6, "launch": "768x768x768 one-view GEMM, 7.08 MB algorithmic (profiles/r01_ncu_gemm64_summary.txt)"},
+    "gemm_kernel<256>": {"bytes": 87.3e6, "launch": "gemm_pair_kernel 15360x3072x1024, 132 MB algorithmic (profiles/r01_ncu_gemm_pair_summary.txt)"},
+    "attn_kernel<QT=2>": {"bytes": 92.0e6, "launch": "render cross-attention 20 views x 15360 keys, 94.4 MB algorithmic (profiles/r01_ncu_attn_final_summary.txt)"},
+    "attn_kernel<QT=1>+combine": {"bytes": 24.8e6, "launch": "update cross-attention 1 view x 7680 keys, 26.0 MB algorithmic (profiles/r01_ncu_attn_update_summary.txt)"},
+}
+
+
 def effective_cores():
     """Host threads for the CPU arm: bounded by sched affinity and the cgroup CPU quota (v2 and v1), then picked by a
     1-second calibration (fp32 2048^3 matmul at 4..64 threads) because oversubscribed boxes run slower with more threads."""
@@ -280,7 +290,8 @@ def main():
         dom = max(tensor_cats, key=lambda c: prof[c]["ms"])
         ach = prof[dom]["flops"] / (prof[dom]["ms"] * 1e-3) / 1e12 if prof[dom]["ms"] > 0 else 0.0
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC.get(dom, {}).get("bytes"), "traffic_of": NCU_TRAFFIC.get(dom, {}).get("launch"),
+                "peak_source": peak_src,
                 "per_kernel": {c: {"ms": round(p["ms"], 3), "launches": p["launches"],
                                    "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["ms"] > 0 and p["flops"] else None,
                                    "frac": round(p["flops"] / (p["ms"] * 1e-3) / 1e12 / peak, 4) if p["ms"] > 0 and p["flops"] else None}

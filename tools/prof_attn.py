@@ -51,6 +51,12 @@ if "upd" in which:           # the one-view update cross-attention alone (ncu ta
     kv = torch.randn(B * Nk, 2 * D, device="cuda").to(dt)
     ms = timeit(lambda: ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk))
     print(f"attn update CA 1 view x M=10 {ms*1e3:9.1f} us  {4.0*B*H*Nq*Nk*64/ms/1e9 if ms else 0:8.1f} TFLOP/s", flush=True)
+if "g64" in which:           # the one-view 768x768x768 GEMM (proj / q / cproj form) alone (ncu target)
+    M = N = K = 768
+    a = torch.randn(M, K, device="cuda").to(dt); w = torch.randn(N, K, device="cuda").to(dt)
+    bias = torch.randn(N, device="cuda"); res = torch.randn(M, N, device="cuda"); out = torch.empty(M, N, device="cuda")
+    ms = timeit(lambda: ops.linear(a, w, bias, residual=res, out=out, w_static=True))
+    print(f"gemm one-view proj 768x768x768 (+bias +fp32 residual) {ms*1e3:9.1f} us  {2.0*M*N*K/ms/1e9 if ms else 0:8.1f} TFLOP/s", flush=True)
 if "gemm" in which:
     for name, (M, N, K) in {
         "enc qkv 20v": (15360, 3072, 1024), "enc proj 20v": (15360, 1024, 1024), "enc fc1 20v": (15360, 4096, 1024),
