@@ -35,10 +35,15 @@ constexpr int HD = 64;
 constexpr int TILE_BYTES = 128 * HD * 2;     // 16 KB
 constexpr float RESCALE_THRESHOLD = 8.0f;    // log2 units
 
-template <int QT> struct AttnCfg {
+// CS = softmax warpgroups per query tile ("column split"): with CS = 2 two warpgroups own the same 128 rows (TMEM lanes)
+// and half of the 128 score columns each, so the per-tile chain  S load -> max -> exp -> P store  of a thread is half
+// as long and twice as many warps hide each other's MUFU / TMEM latencies; the row maximum is exchanged through smem.
+template <int QT, int CS> struct AttnCfg {
   static constexpr int KS = QT == 2 ? 3 : 2;                       // K / V ring depth
-  static constexpr int THREADS = 32 * (4 * QT + 1 + QT);          // softmax warpgroups + TMA warp + one MMA issuer per tile
-  static constexpr int SMEM = (QT + 2 * KS) * TILE_BYTES + 1024 + 256;
+  static constexpr int SM_WARPS = 4 * CS * QT;                     // softmax warps
+  static constexpr int THREADS = 32 * (SM_WARPS + 1 + QT);         // + TMA warp + one MMA issuer per tile
+  static constexpr int XCHG_BYTES = CS == 2 ? QT * 2 * 2 * AT_BM * 4 : 0;   // [tile][parity][half][row] fp32
+  static constexpr int SMEM = (QT + 2 * KS) * TILE_BYTES + 1024 + 256 + XCHG_BYTES;
   static constexpr int TMEM_COLS = QT == 2 ? 512 : 256;
 };
 
@@ -156,14 +161,16 @@ template <bool BF16> __device__ __forceinline__ uint32_t packp(float lo, float h
   return r;
 }
 
-template <bool BF16, int QT, int POLY>
-__global__ void __launch_bounds__(AttnCfg<QT>::THREADS, QT == 1 ? 2 : 1)
+template <bool BF16, int QT, int POLY, int CS>
+__global__ void __launch_bounds__(AttnCfg<QT, CS>::THREADS, QT == 1 ? 2 : 1)
 attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
             const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
             const __grid_constant__ CUtensorMap tmV1, const AttnParams p) {
-  using Cfg = AttnCfg<QT>;
+  using Cfg = AttnCfg<QT, CS>;
   constexpr int KS = Cfg::KS;
-  constexpr int TMA_WARP = 4 * QT, MMA_WARP = 4 * QT + 1;      // issuers: warps MMA_WARP .. MMA_WARP+QT-1
+  constexpr int TMA_WARP = Cfg::SM_WARPS, MMA_WARP = Cfg::SM_WARPS + 1;      // issuers: warps MMA_WARP .. MMA_WARP+QT-1
+  constexpr int NC = AT_BN / CS;                                // score columns per softmax thread
+  constexpr int SMT = 128 * CS;                                 // softmax threads per query tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // QT tiles
@@ -180,6 +187,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   uint64_t* p_full = s_free + 2;       // [2] softmax x -> MMA : P_x(j) stored (and O_x rescaled if needed)
   uint64_t* o_done = p_full + 2;       // [2] MMA -> softmax x : P_x(j) V(j) accumulated into O_x, P columns free again
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  float* xchg = reinterpret_cast<float*>(smem + (QT + 2 * KS) * TILE_BYTES + 256);   // CS == 2 only
 
   M3R_TR(const unsigned long long t_entry = p.trace ? gtime_ns() : 0ull;)
   const int warp = threadIdx.x >> 5;
@@ -205,7 +213,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     if (p.Nk1 > 0) { tma_prefetch_desc(&tmK1); tma_prefetch_desc(&tmV1); }
     mbar_init(q_full, 1);
     for (int s = 0; s < KS; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], nqt); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], nqt); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 128); mbar_init(&p_full[s], 128); mbar_init(&o_done[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_free[s], SMT); mbar_init(&p_full[s], SMT); mbar_init(&o_done[s], 1); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -267,6 +275,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         umma_commit(&o_done[x]);
         umma_commit(&v_empty[st]);
       };
+      M3R_TR(unsigned long long* trm = (p.trace && x == 0) ? p.trace + 128ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) + 64 : nullptr;)
       mbar_wait(q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
@@ -274,34 +283,40 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) {
           mbar_wait(&k_full[(j + 1) % KS], ((j + 1) / KS) & 1);
+          M3R_TR(if (trm && j < 12) trm[4 * j] = gtime_ns();)
           mbar_wait(&s_free[x], j & 1);                          // softmax holds S(j) in registers
+          M3R_TR(if (trm && j < 12) trm[4 * j + 1] = gtime_ns();)
           tc_fence_after();
           issue_qk(j + 1);                                       // runs under the exponentials of tile j
         }
         mbar_wait(&v_full[j % KS], (j / KS) & 1);
         mbar_wait(&p_full[x], j & 1);
+        M3R_TR(if (trm && j < 12) trm[4 * j + 2] = gtime_ns();)
         tc_fence_after();
         issue_pv(j);
+        M3R_TR(if (trm && j < 12) trm[4 * j + 3] = gtime_ns();)
       }
     }
-  } else if (warp < 4 * nqt) {
-    // ------------------------------------------------------------------ softmax warpgroup x
-    const int x = warp >> 2;
-    const int quarter = warp & 3;
+  } else if (warp < 4 * CS * nqt) {
+    // ------------------------------------------------------------------ softmax warpgroup(s) of query tile x
+    const int x = warp / (4 * CS);
+    const int half = (warp % (4 * CS)) >> 2;     // which NC-column half of the score tile (always 0 when CS == 1)
+    const int quarter = warp & 3;                // TMEM lane quarter = warp id % 4
     const int lane = threadIdx.x & 31;
     const int row = quarter * 32 + lane;
     const int q_idx = q0 + x * AT_BM + row;
     const uint32_t lane_addr = tmem_base + (uint32_t(quarter * 32) << 16);
-    const uint32_t s_addr = lane_addr + x * 256;
-    const uint32_t p_addr = s_addr + 128;
-    const uint32_t o_addr = s_addr + 192;
+    const uint32_t s_addr = lane_addr + x * 256 + half * NC;
+    const uint32_t p_addr = lane_addr + x * 256 + 128 + half * (NC / 2);
+    const uint32_t o_addr = lane_addr + x * 256 + 192 + half * (HD / CS);
+    float* xq = xchg + x * (2 * 2 * AT_BM);      // [parity][half][row]
     float m_used = -INFINITY;      // max currently folded into the exponent (raw score units)
     float l_run = 0.f;
     const PolyC polyc = make_polyc();
 
     M3R_TR(unsigned long long* tr = nullptr;
-           if (p.trace && row == 0 && x == 0)
-             tr = p.trace + 64ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
+           if (p.trace && row == 0 && x == 0 && half == 0)
+             tr = p.trace + 128ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x);
            if (tr) { tr[0] = t_entry; tr[1] = gtime_ns(); tr[2] = smid(); tr[3] = (unsigned long long)n_tiles; })
     int j = 0;
     for (; j < n_tiles; ++j) {
@@ -309,32 +324,39 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       mbar_wait(&s_full[x], j & 1);
       M3R_TR(if (tr && j < 12) tr[8 + 4 * j] = gtime_ns();)
       tc_fence_after();
-      uint32_t raw[128];
-      tmem_ld32(s_addr, *reinterpret_cast<uint32_t(*)[32]>(&raw[0]));
-      tmem_ld32(s_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[32]));
-      tmem_ld32(s_addr + 64, *reinterpret_cast<uint32_t(*)[32]>(&raw[64]));
-      tmem_ld32(s_addr + 96, *reinterpret_cast<uint32_t(*)[32]>(&raw[96]));
+      uint32_t raw[NC];
+#pragma unroll
+      for (int c = 0; c < NC / 32; ++c) tmem_ld32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&raw[c * 32]));
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&s_free[x]);                     // Q K^T of the next tile may overwrite S now
       M3R_TR(if (tr && j < 12) tr[9 + 4 * j] = gtime_ns();)
       if (it.mask) {
 #pragma unroll
-        for (int c = 0; c < 128; ++c) {
-          const int g = it.g0 + c;
-          const bool ok = c < it.nvalid && !(g >= lo && g < hi);
+        for (int c = 0; c < NC; ++c) {
+          const int lc = half * NC + c;
+          const int g = it.g0 + lc;
+          const bool ok = lc < it.nvalid && !(g >= lo && g < hi);
           if (!ok) raw[c] = 0xff800000u;            // -inf
         }
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 128; c += 4) {
+      for (int c = 0; c < NC; c += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(raw[c]));
         mx1 = fmaxf(mx1, __uint_as_float(raw[c + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(raw[c + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(raw[c + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      if (CS == 2) {
+        // the two threads of a row agree on the row maximum (hence on m_used and on every rescale decision); the buffer
+        // alternates with the tile parity, so a thread one tile ahead never overwrites a value its partner still reads
+        float* e = xq + (j & 1) * (2 * AT_BM);
+        e[half * AT_BM + row] = mx;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + x), "n"(SMT) : "memory");
+        mx = fmaxf(mx, e[(half ^ 1) * AT_BM + row]);
+      }
       // lazy rescaling: refresh the folded max only when it is stale by more than 2^8
       float alpha = 1.f;
       bool refresh = false;
@@ -351,7 +373,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         tc_fence_after();
         if (__any_sync(0xffffffffu, refresh)) {
 #pragma unroll 1
-          for (int c = 0; c < 8; ++c) {               // rare path: small chunks keep the register footprint low
+          for (int c = 0; c < 8 / CS; ++c) {          // rare path: small chunks keep the register footprint low
             uint32_t o[8];
             tmem_ld8(o_addr + c * 8, o);
             tmem_wait_ld();
@@ -367,7 +389,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       const uint64_t sl2_2 = pk2(p.sl2, p.sl2), nmoff2 = pk2(-moff, -moff);
       uint64_t rs0 = pk2(0.f, 0.f), rs1 = rs0;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < NC / 32; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
@@ -397,49 +419,58 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     }
     M3R_TR(if (tr) tr[4] = gtime_ns();)
 
-    // ---- epilogue: wait for the last P V, normalise, store
-    uint32_t accr[HD];
+    // ---- epilogue: wait for the last P V, normalise, store (each thread: its row, HD / CS of the 64 output columns)
+    constexpr int OC = HD / CS;
+    uint32_t accr[OC];
     if (j > 0) {
       mbar_wait(&o_done[x], (j - 1) & 1);      // last P V (every earlier phase was waited for in the loop)
       tc_fence_after();
-      tmem_ld32(o_addr, *reinterpret_cast<uint32_t(*)[32]>(&accr[0]));
-      tmem_ld32(o_addr + 32, *reinterpret_cast<uint32_t(*)[32]>(&accr[32]));
+#pragma unroll
+      for (int c = 0; c < OC / 32; ++c) tmem_ld32(o_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&accr[c * 32]));
       tmem_wait_ld();
     } else {
 #pragma unroll
-      for (int d = 0; d < HD; ++d) accr[d] = 0u;
+      for (int d = 0; d < OC; ++d) accr[d] = 0u;
     }
-    float acc[HD];
+    if (CS == 2) {
+      // row sum = sum of the two halves (added in a fixed order so both threads hold the same value); the buffer of the
+      // parity n_tiles & 1 was last read two tiles ago
+      float* e = xq + (n_tiles & 1) * (2 * AT_BM);
+      e[half * AT_BM + row] = l_run;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + x), "n"(SMT) : "memory");
+      l_run = e[row] + e[AT_BM + row];
+    }
+    float acc[OC];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = __uint_as_float(accr[d]);
-    if (q_idx < p.Nq) {
+    for (int d = 0; d < OC; ++d) acc[d] = __uint_as_float(accr[d]);
+    if (q_idx < p.Nq && p.splits == 1) {
       const long long grow = (long long)b * p.Nq + q_idx;
-      if (p.splits == 1) {
-        const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD);
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD + half * OC);
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          uint4 w;
-          w.x = packp<BF16>(acc[8 * t] * inv, acc[8 * t + 1] * inv);
-          w.y = packp<BF16>(acc[8 * t + 2] * inv, acc[8 * t + 3] * inv);
-          w.z = packp<BF16>(acc[8 * t + 4] * inv, acc[8 * t + 5] * inv);
-          w.w = packp<BF16>(acc[8 * t + 6] * inv, acc[8 * t + 7] * inv);
-          o4[t] = w;
-        }
+      for (int t = 0; t < OC / 8; ++t) {
+        uint4 w;
+        w.x = packp<BF16>(acc[8 * t] * inv, acc[8 * t + 1] * inv);
+        w.y = packp<BF16>(acc[8 * t + 2] * inv, acc[8 * t + 3] * inv);
+        w.z = packp<BF16>(acc[8 * t + 4] * inv, acc[8 * t + 5] * inv);
+        w.w = packp<BF16>(acc[8 * t + 6] * inv, acc[8 * t + 7] * inv);
+        o4[t] = w;
       }
     }
     // key-range splits: unnormalised partial (O, m, l) of this CTA.  Layout [split][unit = (b, h, query tile)][16 column
     // chunks][128 rows] float4 (and [split][unit][128 rows] float2): lanes are consecutive rows, so both these stores and
     // the merge's loads are fully coalesced 512 B requests.
+    constexpr int CH = 16 / CS;                   // float4 column chunks per thread
     const int n_qtiles = (p.Nq + AT_BM - 1) / AT_BM;
     const long long unit = ((long long)b * p.H + h) * n_qtiles + (q0 / AT_BM + x);
     const long long n_units = (long long)gridDim.z / p.splits * p.H * n_qtiles;
     if (p.splits > 1) {
-      float4* o4 = reinterpret_cast<float4*>(p.part_o) + ((long long)split * n_units + unit) * (16 * AT_BM) + row;
+      float4* o4 = reinterpret_cast<float4*>(p.part_o) + ((long long)split * n_units + unit) * (16 * AT_BM) + (half * CH) * AT_BM + row;
 #pragma unroll
-      for (int t = 0; t < 16; ++t) o4[t * AT_BM] = make_float4(acc[4 * t], acc[4 * t + 1], acc[4 * t + 2], acc[4 * t + 3]);
-      reinterpret_cast<float2*>(p.part_ml)[((long long)split * n_units + unit) * AT_BM + row] =
-          make_float2(m_used == -INFINITY ? -INFINITY : m_used * p.sl2, l_run);
+      for (int t = 0; t < CH; ++t) o4[t * AT_BM] = make_float4(acc[4 * t], acc[4 * t + 1], acc[4 * t + 2], acc[4 * t + 3]);
+      if (half == 0)
+        reinterpret_cast<float2*>(p.part_ml)[((long long)split * n_units + unit) * AT_BM + row] =
+            make_float2(m_used == -INFINITY ? -INFINITY : m_used * p.sl2, l_run);
     }
     M3R_TR(if (tr) tr[5] = gtime_ns();)
     if (p.splits > 1) {
@@ -447,27 +478,27 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
       // out = sum_s O_s 2^(m_s - m) / sum_s l_s 2^(m_s - m).  No extra kernel launch on the one-view-per-step chain.
       __shared__ int s_last[2];
       __threadfence();                                              // partials visible device-wide
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");    // the 4 warps of this warpgroup
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + x), "n"(SMT) : "memory");    // the softmax threads of this query tile
       int* cnt = p.split_cnt + unit;
-      if (row == 0) {
+      if (row == 0 && half == 0) {
         const int prev = atomicAdd(cnt, 1);
         s_last[x] = (prev == p.splits - 1);
         if (prev == p.splits - 1) *cnt = 0;                         // self-cleaning for the next launch
       }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + x) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + x), "n"(SMT) : "memory");
       if (s_last[x]) {
         __threadfence();
         const float2* mlp = reinterpret_cast<const float2*>(p.part_ml) + unit * AT_BM + row;
-        const float4* op = reinterpret_cast<const float4*>(p.part_o) + unit * (16 * AT_BM) + row;
+        const float4* op = reinterpret_cast<const float4*>(p.part_o) + unit * (16 * AT_BM) + (half * CH) * AT_BM + row;
         const long long ml_stride = n_units * AT_BM, o_stride = n_units * (16 * AT_BM);
         float m = -INFINITY;
 #pragma unroll 4
         for (int sp = 0; sp < p.splits; ++sp) m = fmaxf(m, __ldcg(mlp + sp * ml_stride).x);
         float l = 0.f;
         const long long grow = (long long)b * p.Nq + q_idx;
-        // a quarter of the 64 columns at a time: 4 splits x 4 float4 loads in flight per thread, few L2 round trips
+        // 16 columns at a time: 4 splits x 4 float4 loads in flight per thread, few L2 round trips
 #pragma unroll 1
-        for (int qd = 0; qd < 4; ++qd) {
+        for (int qd = 0; qd < CH / 4; ++qd) {
           float a16[16];
 #pragma unroll
           for (int d = 0; d < 16; ++d) a16[d] = 0.f;
@@ -492,9 +523,9 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
               }
             }
           }
-          const float inv = l > 0.f ? 1.0f / l : 0.f;      // l is complete after the first quarter
+          const float inv = l > 0.f ? 1.0f / l : 0.f;      // l is complete after the first pass
           if (q_idx < p.Nq) {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD + qd * 16);
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD + half * OC + qd * 16);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
               uint4 wv;
@@ -511,7 +542,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
 
   M3R_TR(if (p.trace && threadIdx.x == 0)
-           p.trace[64ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) + 6] = gtime_ns();)
+           p.trace[128ull * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) + 6] = gtime_ns();)
   tc_fence_before();
   __syncthreads();
   if (warp == MMA_WARP) {
@@ -520,18 +551,18 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   }
 }
 
-template <bool BF16, int QT, int POLY>
+template <bool BF16, int QT, int POLY, int CS>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                        const CUtensorMap& tmV1, const AttnParams& p, int B, cudaStream_t s) {
-  using Cfg = AttnCfg<QT>;
+  using Cfg = AttnCfg<QT, CS>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<BF16, QT, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<BF16, QT, POLY, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((p.Nq + QT * AT_BM - 1) / (QT * AT_BM), p.H, B * p.splits);
-  cudaError_t e = launch_pdl(attn_kernel<BF16, QT, POLY>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, tmQ, tmK0, tmV0, tmK1, tmV1, p);
+  cudaError_t e = launch_pdl(attn_kernel<BF16, QT, POLY, CS>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, tmQ, tmK0, tmV0, tmK1, tmV1, p);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("attention launch: %s", cudaGetErrorString(e));
   count_launch();
@@ -631,11 +662,18 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     // (the softmax warps become issue-bound); 1 of 8 is the shipped default.
     static int poly = -1;
     if (poly < 0) { const char* e = getenv("M3R_ATTN_POLY"); poly = e ? atoi(e) : 1; if (poly < 0 || poly > 3) poly = 1; }
+    // softmax warpgroups per query tile (column split).  Measured (profiles/r01_attention_variants.txt, run 27): CS=2 is 10 %
+    // slower on the render shape and equal on the one-view shapes (the softmax is issue-bound, not latency-bound: the extra
+    // max exchange + barrier per tile costs more than the added warps hide) -> 1 by default, M3R_ATTN_CS=2 selects it
+    int colsplit = 1;
+    if (const char* e = getenv("M3R_ATTN_CS")) { if (atoi(e) == 2) colsplit = 2; }
     int rc;
-#define M3R_LAUNCH_ATTN(BF, QTV) (poly == 0 ? launch_attn<BF, QTV, 0>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
-                                  : poly == 1 ? launch_attn<BF, QTV, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
-                                  : poly == 2 ? launch_attn<BF, QTV, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
-                                              : launch_attn<BF, QTV, 3>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs))
+#define M3R_LAUNCH_ATTN(BF, QTV) (colsplit == 2 ? (poly == 0 ? launch_attn<BF, QTV, 0, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
+                                                       : launch_attn<BF, QTV, 1, 2>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs)) \
+                                  : poly == 0 ? launch_attn<BF, QTV, 0, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
+                                  : poly == 1 ? launch_attn<BF, QTV, 1, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
+                                  : poly == 2 ? launch_attn<BF, QTV, 2, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs) \
+                                              : launch_attn<BF, QTV, 3, 1>(tmQ, tmK0, tmV0, tmK1, tmV1, p, a->B, cs))
     if (a->is_bf16) rc = qt == 2 ? M3R_LAUNCH_ATTN(true, 2) : M3R_LAUNCH_ATTN(true, 1);
     else rc = qt == 2 ? M3R_LAUNCH_ATTN(false, 2) : M3R_LAUNCH_ATTN(false, 1);
 #undef M3R_LAUNCH_ATTN

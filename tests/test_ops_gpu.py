@@ -236,12 +236,15 @@ def test_memory_cross_attention(dtype, Nm, n, N):
 
 
 @pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("cs", [1, 2])
 @pytest.mark.parametrize("qt,splits", [(1, 1), (1, 3), (1, 16), (2, 1), (2, 2), (2, 7)])
-def test_attention_kernel_variants(dtype, qt, splits, monkeypatch):
-    """Force each kernel configuration (1 or 2 query tiles per CTA, key-range splits + combine) on a masked,
-    two-segment, ragged problem and on a long-key problem with large score spread (exercises the lazy rescale)."""
+def test_attention_kernel_variants(dtype, qt, splits, cs, monkeypatch):
+    """Force each kernel configuration (1 or 2 query tiles per CTA, 1 or 2 softmax warpgroups per query tile, key-range
+    splits + in-kernel merge) on a masked, two-segment, ragged problem and on a long-key problem with large score spread
+    (exercises the lazy rescale)."""
     monkeypatch.setenv("M3R_ATTN_QT", str(qt))
     monkeypatch.setenv("M3R_ATTN_SPLITS", str(splits))
+    monkeypatch.setenv("M3R_ATTN_CS", str(cs))
     B, H, n, N, Nm = 1, 3, 2, 300, 700
     D = H * 64
     mem = rnd(B, Nm, 2 * D, dtype=dtype, seed=30)

@@ -20,7 +20,7 @@ fn(); fn()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 lib = _lib.lib()
 for cold in (True, False):
-    buf = torch.zeros(64 * 4096, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(128 * 4096, dtype=torch.int64, device="cuda")
     if cold:
         flush.zero_()
     torch.cuda.synchronize()
@@ -28,7 +28,7 @@ for cold in (True, False):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); fn(); b.record(); torch.cuda.synchronize()
     lib.m3r_debug_trace(None)
-    t = buf.view(-1, 64).cpu()
+    t = buf.view(-1, 128).cpu()
     t = t[t[:, 0] != 0]
     t0 = int(t[:, 0].min())
     rel = lambda v: (int(v) - t0) / 1e3  # noqa: E731
@@ -55,5 +55,9 @@ for cold in (True, False):
             s = [int(v) for v in r[8 + 4 * j: 12 + 4 * j]]
             if j == 0:
                 s[2] = s[1]
-            print(f"      j={j:2d}: {(s[0]-prev)/1e3:6.2f} | {(s[1]-s[0])/1e3:5.2f} | {(s[2]-s[1])/1e3:5.2f} | {(s[3]-s[2])/1e3:5.2f}")
+            mm = [int(v) for v in r[64 + 4 * j: 68 + 4 * j]]          # MMA thread: k_full ok, s_free ok (QK j+1 issued), p_full ok, PV j issued
+            base = s[0]                                                # everything relative to this tile's s_full wait end
+            mrel = " ".join(f"{(v - base) / 1e3:6.2f}" if v else "   n/a" for v in mm)
+            print(f"      j={j:2d}: {(s[0]-prev)/1e3:6.2f} | {(s[1]-s[0])/1e3:5.2f} | {(s[2]-s[1])/1e3:5.2f} | {(s[3]-s[2])/1e3:5.2f}"
+                  f"   || MMA thread rel. to S(j) ready: k_full(j+1) {mrel.split()[0]}  s_free(j)/QK(j+1) {mrel.split()[1]}  p_full(j) {mrel.split()[2]}  PV(j) issued {mrel.split()[3]}")
             prev = s[3]
