@@ -365,32 +365,14 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
         alpha = (m_used == -INFINITY) ? 0.f : ex2((m_used - mx) * p.sl2);
         m_used = mx;
       }
-      if (j > 0) {
-        // P V (j-1) must have consumed the P columns (and landed in O) before they are rewritten / O is rescaled.
-        // Every phase of o_done is waited for, in order, so the parity wait is exact.
-        mbar_wait(&o_done[x], (j - 1) & 1);
-        M3R_TR(if (tr && j < 12) tr[10 + 4 * j] = gtime_ns();)
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, refresh)) {
-#pragma unroll 1
-          for (int c = 0; c < 8 / CS; ++c) {          // rare path: small chunks keep the register footprint low
-            uint32_t o[8];
-            tmem_ld8(o_addr + c * 8, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int d = 0; d < 8; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
-            tmem_st8(o_addr + c * 8, o);
-          }
-          tmem_wait_st();
-        }
-      }
       l_run *= alpha;
       const float moff = (m_used == -INFINITY) ? 0.f : m_used * p.sl2;
       const uint64_t sl2_2 = pk2(p.sl2, p.sl2), nmoff2 = pk2(-moff, -moff);
       uint64_t rs0 = pk2(0.f, 0.f), rs1 = rs0;
+      // all exponentials of the tile first (the packed P values replace the scores in registers) ...
+      uint32_t pk[NC / 2];
 #pragma unroll
       for (int c = 0; c < NC / 32; ++c) {
-        uint32_t pk[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) {
           const uint64_t v = fma2(pk2(__uint_as_float(raw[c * 32 + 2 * t]), __uint_as_float(raw[c * 32 + 2 * t + 1])), sl2_2, nmoff2);
@@ -404,10 +386,31 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             a1 = ex2(x1);
           }
           if (t & 1) rs1 = add2(rs1, pk2(a0, a1)); else rs0 = add2(rs0, pk2(a0, a1));
-          pk[t] = packp<BF16>(a0, a1);
+          pk[c * 16 + t] = packp<BF16>(a0, a1);
         }
-        tmem_st16(p_addr + c * 16, pk);
       }
+      // ... and only then the wait for P V (j-1): it must have consumed the P columns (and landed in O) before they are
+      // rewritten / O is rescaled, but its latency is now hidden behind the exponentials above instead of stalling the
+      // warpgroup between the row maximum and the first ex2.  Every phase of o_done is waited for, in order, so the
+      // parity wait is exact.
+      if (j > 0) {
+        mbar_wait(&o_done[x], (j - 1) & 1);
+        M3R_TR(if (tr && j < 12) tr[10 + 4 * j] = gtime_ns();)
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, refresh)) {
+#pragma unroll 1
+          for (int c = 0; c < 8 / CS; ++c) {          // rare path: small chunks keep the register footprint low
+            uint32_t o[8];
+            tmem_ld8(o_addr + c * 8, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int d = 0; d < 8; ++d) o[d] = __float_as_uint(__uint_as_float(o[d]) * alpha);
+            tmem_st8(o_addr + c * 8, o);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC / 32; ++c) tmem_st16(p_addr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&pk[c * 16]));
       float r0, r1, r2, r3;
       up2(rs0, r0, r1);
       up2(rs1, r2, r3);

@@ -14,18 +14,30 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // One warp per row; the row lives in registers (D <= 32 * 4 * MAXV). Two-pass mean / variance like torch.
-template <int MAXV, bool IN16>
+template <int MAXV, bool IN16, bool PRE>
 __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ xv, long long ldx,
                                                         const float* __restrict__ add, long long ldadd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int M, int D, void* __restrict__ out, long long ldo,
                                                         int out_dtype, int is_bf16) {
-  griddep_wait();
-  griddep_launch();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;  // float4 per row
+  // PRE (small, latency-bound launches of the one-view chain): gamma / beta are weights, so they are fetched before the
+  // programmatic-dependency wait, under the previous kernel's tail.  Large launches keep their registers for occupancy.
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  float4 gv[PRE ? MAXV : 1], bv[PRE ? MAXV : 1];
+  if (PRE) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int idx = lane + i * 32;
+      if (idx < nv) { gv[i] = __ldg(g4 + idx); bv[i] = __ldg(b4 + idx); }
+    }
+  }
+  griddep_wait();
+  griddep_launch();
+  if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xv) + (IN16 ? 0 : (long long)row * ldx));
   const uint2* xh = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(xv) + (IN16 ? (long long)row * ldx : 0));
   const float4* ar = add ? reinterpret_cast<const float4*>(add + (long long)row * ldadd) : nullptr;
@@ -60,13 +72,11 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / D + eps);
-  const float4* g4 = reinterpret_cast<const float4*>(gamma);
-  const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + i * 32;
     if (idx < nv) {
-      const float4 g = __ldg(g4 + idx), b = __ldg(b4 + idx);
+      const float4 g = PRE ? gv[PRE ? i : 0] : __ldg(g4 + idx), b = PRE ? bv[PRE ? i : 0] : __ldg(b4 + idx);
       float4 y;
       y.x = (v[i].x - mean) * rstd * g.x + b.x;
       y.y = (v[i].y - mean) * rstd * g.y + b.y;
@@ -245,10 +255,12 @@ extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int6
   const int wpb = M <= 4096 ? 4 : 8;          // small row counts: more, smaller blocks cover more SMs
   const int grid = (M + wpb - 1) / wpb;
   ProfScope prof(PROF_LN, 0.0, (double)M * D * (4.0 + (add ? 4.0 : 0.0) + (out_dtype ? 2.0 : 4.0)), s);
-  if (D <= 1024)
-    launch_pdl(layernorm_kernel<8, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
+  if (D <= 1024 && M <= 4096)
+    launch_pdl(layernorm_kernel<8, false, true>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
+  else if (D <= 1024)
+    launch_pdl(layernorm_kernel<8, false, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
   else
-    launch_pdl(layernorm_kernel<16, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
+    launch_pdl(layernorm_kernel<16, false, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
   return check_launch("layernorm");
 }
 
@@ -263,9 +275,9 @@ extern "C" int m3r_layernorm16(const void* x16, int64_t ldx, const float* gamma,
   ProfScope prof(PROF_LN, 0.0, (double)M * D * 4.0, s);
   const float* none = nullptr;
   if (D <= 1024)
-    launch_pdl(layernorm_kernel<8, true>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16);
+    launch_pdl(layernorm_kernel<8, true, false>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16);
   else
-    launch_pdl(layernorm_kernel<16, true>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16);
+    launch_pdl(layernorm_kernel<16, true, false>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16);
   return check_launch("layernorm16");
 }
 

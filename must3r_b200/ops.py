@@ -89,12 +89,29 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out
 
 
-def cast16(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+def layernorm16(x16: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
+    """LayerNorm of 16-bit rows -> 16-bit rows of the same format (memory_mode 'raw': norm_y applied at use)."""
+    _req_cuda(x16)
+    assert x16.dtype in F16 and x16.dim() == 2 and x16.stride(1) == 1
+    M, D = x16.shape
+    out = torch.empty((M, D), device=x16.device, dtype=x16.dtype)
+    _lib.check(_lib.lib().m3r_layernorm16(_p(x16), x16.stride(0), _p(gamma), _p(beta), eps, M, D, _p(out), out.stride(0),
+                                          F16[x16.dtype], _stream()), "layernorm16")
+    return out
+
+
+def cast16(x: torch.Tensor, dtype: torch.dtype, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [M,D] (+ optional fp32 `add`) -> 16-bit."""
     _req_cuda(x)
     assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
     out = torch.empty(x.shape, device=x.device, dtype=dtype)
-    _lib.check(_lib.lib().m3r_cast16(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(out), out.stride(0), F16[dtype],
-                                     _stream()), "cast16")
+    if add is None:
+        _lib.check(_lib.lib().m3r_cast16(_p(x), x.stride(0), x.shape[0], x.shape[1], _p(out), out.stride(0), F16[dtype],
+                                         _stream()), "cast16")
+    else:
+        assert add.dtype == torch.float32 and add.shape == x.shape and add.stride(1) == 1
+        _lib.check(_lib.lib().m3r_add_cast16(_p(x), x.stride(0), _p(add), add.stride(0), x.shape[0], x.shape[1], _p(out),
+                                             out.stride(0), F16[dtype], _stream()), "add_cast16")
     return out
 
 

@@ -181,6 +181,22 @@ def test_layernorm(out_dtype, D):
     assert rel_l2(out, torch.nn.functional.layer_norm(x + add, (D,), g, b, 1e-5)) < OUT_TOL[out_dtype]
 
 
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("M,D", [(333, 768), (5000, 768), (100, 1024), (64, 128)])
+def test_layernorm16_and_add_cast16(dtype, M, D):
+    """16-bit-in LayerNorm and fp32 (x + add) -> 16-bit cast (memory_mode 'raw' / 'norm_y' building blocks), small and
+    large launches (the small ones preload gamma / beta before the dependency wait)."""
+    x, add = rnd(M, D, seed=15, scale=3.0) + 0.5, rnd(M, D, seed=16)
+    g, b = 1 + 0.1 * rnd(D, seed=17), 0.1 * rnd(D, seed=18)
+    x16 = x.to(dtype)
+    out = ops.layernorm16(x16, g, b, 1e-6)
+    assert out.dtype == dtype and rel_l2(out, torch.nn.functional.layer_norm(x16.float(), (D,), g, b, 1e-6)) < OUT_TOL[dtype]
+    assert torch.equal(ops.cast16(x, dtype), x.to(dtype))
+    assert torch.equal(ops.cast16(x, dtype, add=add), (x + add).to(dtype))
+    out = ops.layernorm(x, g, b, 1e-6, out_dtype=dtype)
+    assert rel_l2(out, torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)) < OUT_TOL[dtype]
+
+
 def ref_attn(q, k, v, mask=None):
     s = (q.float() @ k.float().transpose(-1, -2)) * 0.125
     if mask is not None:

@@ -94,7 +94,10 @@ def test_world2_gloo_matches_composed_oracle():
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as so:           # a port the kernel says is free right now (fixed numbers collide now and then)
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
