@@ -84,6 +84,23 @@ class ClockSampler:
         self.t = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        """NVML every 40 ms (a 5-step timed region is ~0.3 s); nvidia-smi every 200 ms if NVML is not importable."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [(0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")]
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                r = int(get_reasons(h))
+                flags = {n: ("Active" if r & b else "Not Active") for b, n in bits}
+                self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx), flags["hw_slowdown"],
+                                  flags["hw_thermal_slowdown"], flags["sw_thermal_slowdown"], flags["sw_power_cap"]])
+                self._stop.wait(0.04)
+            return
+        except Exception:  # noqa: BLE001
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
