@@ -47,7 +47,7 @@ NCU_TRAFFIC = {
     "gemm_kernel<64>": {"bytes": 4.76e6, "launch": "768x768x768 one-view GEMM, 7.08 MB algorithmic (profiles/r01_ncu_gemm64_summary.txt)"},
     "gemm_kernel<256>": {"bytes": 87.3e6, "launch": "gemm_pair_kernel 15360x3072x1024, 132 MB algorithmic (profiles/r01_ncu_gemm_pair_summary.txt)"},
     "attn_kernel<QT=2>": {"bytes": 92.0e6, "launch": "render cross-attention 20 views x 15360 keys, 94.4 MB algorithmic (profiles/r01_ncu_attn_final_summary.txt)"},
-    "attn_kernel<QT=1>+combine": {"bytes": 24.8e6, "launch": "update cross-attention 1 view x 7680 keys, 26.0 MB algorithmic (profiles/r01_ncu_attn_update_summary.txt)"},
+    "attn_kernel<QT=1>+split-merge": {"bytes": 24.8e6, "launch": "update cross-attention 1 view x 7680 keys, 26.0 MB algorithmic (profiles/r01_ncu_attn_update_summary.txt)"},
 }
 
 
@@ -290,7 +290,7 @@ def main():
         buf = (C.c_double * 28)()
         lib.m3r_prof_read(buf)
         lib.m3r_prof_enable(0)
-        cats = ["gemm_kernel<256>", "gemm_kernel<128>", "gemm_kernel<64>", "attn_kernel<QT=2>", "attn_kernel<QT=1>+combine",
+        cats = ["gemm_kernel<256>", "gemm_kernel<128>", "gemm_kernel<64>", "attn_kernel<QT=2>", "attn_kernel<QT=1>+split-merge",
                 "layernorm_kernel", "other"]
         prof = {c: {"ms": buf[i * 4], "launches": int(buf[i * 4 + 1]), "flops": buf[i * 4 + 2], "bytes": buf[i * 4 + 3]}
                 for i, c in enumerate(cats)}

@@ -40,7 +40,7 @@ long long m3r_launch_count(void);
 /* Optional per-kernel device timing for bench.py: CUDA events are recorded on the launch stream around every
  * GEMM / attention / LayerNorm kernel while enabled.  m3r_prof_read synchronises and fills
  * out[cat*4 + {0: ms, 1: launches, 2: algorithmic flops, 3: algorithmic bytes}] for the 7 categories
- * gemm_kernel<256>, gemm_kernel<128>, gemm_kernel<64>, attn_kernel<QT=2>, attn_kernel<QT=1> (+combine), layernorm,
+ * gemm_kernel<256>, gemm_kernel<128>, gemm_kernel<64>, attn_kernel<QT=2>, attn_kernel<QT=1> (key splits merged in-kernel), layernorm,
  * other (28 doubles). */
 void m3r_prof_enable(int on);
 int m3r_prof_read(double* out);

@@ -3,7 +3,8 @@
 // One CTA = one (batch, head, QT x 128 queries [, key split]).  QT = 2 for throughput shapes: the two query tiles
 // share every K / V tile that TMA brings in (half the L2->smem traffic) and ping-pong on the tensor pipe, so one
 // tile's softmax overlaps the other's MMAs.  Roles:
-//   warps 0..4*QT-1 : softmax warpgroup per query tile -- ONE query row per thread (TMEM lane == row, so row max /
+//   warps 0..4*QT-1 : (4*CS*QT warps with the optional column-split variant, see AttnCfg) softmax warpgroup per
+//                     query tile -- ONE query row per thread (TMEM lane == row, so row max /
 //                     row sum need no shuffles); single pass over a 128-key S row held in registers: row max, exp2
 //                     with the scale folded in, row sum, pack P to 16-bit into its own TMEM columns.  As soon as
 //                     the row is in registers the S columns are handed back, so Q K^T of tile j+1 runs under the
