@@ -219,25 +219,109 @@ def inference_multi_ar_batch(encoder, decoder, imgs, true_shape, mem=None, verbo
 
 
 # --------------------------------------------------------------------------------------------- memory edits by label
+# The engine edits the memory between decoder calls (eviction of frames that left the window, refresh of keyframes).
+# The reference does it with boolean masks computed on the device (engine/inference.py:205-228): every mask indexing is a
+# host sync plus a copy of the whole memory, per level.  The label of every token is known on the host (the decoder
+# hands them out deterministically, decoder.py:242-247), so a host-side copy of the label row ("shadow") rides along on
+# the label tensor; with it the edits become slice operations: no sync, and dropping the most recent frame - what a
+# non-keyframe step of the streaming schedule does - is a zero-copy prefix view.  Without a shadow (a memory of unknown
+# provenance, or scenes with different label rows) the reference's device path runs.
+def _host_labels(mem_labels):
+    sh = getattr(mem_labels, "_m3r_labels_host", None)
+    if sh is None or mem_labels.dim() != 2 or mem_labels.shape[0] != 1 or sh.shape[0] != mem_labels.shape[1]:
+        return None
+    return sh
+
+
+def _set_host_labels(mem_labels, shadow):
+    try:
+        mem_labels._m3r_labels_host = shadow
+    except Exception:  # noqa: BLE001  (tensor subclasses that refuse attributes)
+        pass
+    return mem_labels
+
+
+def _runs(mask):
+    """[(start, stop)] of the True runs of a 1-D bool array."""
+    if mask.size == 0:
+        return []
+    edges = np.flatnonzero(np.diff(np.concatenate(([False], mask, [False])).astype(np.int8)))
+    return list(zip(edges[0::2].tolist(), edges[1::2].tolist()))
+
+
+def _shadow_after_call(mem_before, new_mem, idx_st, x_st):
+    """Attach the host label row to the memory a decoder update call returned: previous row + for every aspect-ratio
+    group, in call order, the labels mem_nimgs + k repeated over the view's N tokens (decoder.py:237-247)."""
+    prev = np.zeros((0,), dtype=np.int64) if mem_before is None else _host_labels(mem_before[1])
+    if prev is None or new_mem[1].dim() != 2 or new_mem[1].shape[0] != 1:
+        return new_mem
+    first = 0 if mem_before is None else int(mem_before[2])
+    parts, off = [prev], 0
+    for ids, xg in zip(idx_st, x_st):
+        nv, N = len(ids), int(xg.shape[-2])
+        parts.append(np.repeat(np.arange(first + off, first + off + nv, dtype=np.int64), N))
+        off += nv
+    sh = np.concatenate(parts)
+    if sh.shape[0] == new_mem[1].shape[1]:
+        _set_host_labels(new_mem[1], sh)
+    return new_mem
+
+
 def _remove_from_mem(mem_values, mem_labels, idx):
     """Drop every token labelled idx (engine/inference.py:205-213)."""
-    keep = mem_labels != idx
-    B, _, D = mem_values[0].shape
-    return [v[keep].view(B, -1, D) for v in mem_values], mem_labels[keep].view(B, -1)
+    sh = _host_labels(mem_labels)
+    if sh is None:
+        keep = mem_labels != idx
+        B, _, D = mem_values[0].shape
+        return [v[keep].view(B, -1, D) for v in mem_values], mem_labels[keep].view(B, -1)
+    keep = sh != idx
+    runs = _runs(keep)
+    if len(runs) == 1 and runs[0] == (0, sh.shape[0]):
+        return mem_values, mem_labels
+    if len(runs) <= 1 and (not runs or runs[0][0] == 0):
+        stop = runs[0][1] if runs else 0                       # the dropped tokens are the tail: prefix views, no copy
+        values, labels = [v[:, :stop] for v in mem_values], mem_labels[:, :stop]
+    else:
+        values = [torch.cat([v[:, a:b] for a, b in runs], dim=1) for v in mem_values]
+        labels = torch.cat([mem_labels[:, a:b] for a, b in runs], dim=1)
+    return values, _set_host_labels(labels, sh[keep])
 
 
 def _restore_label_in_mem(mem_labels, old_idx_to_restore, new_idx_to_remove):
     """engine/inference.py:216-219"""
+    sh = _host_labels(mem_labels)
     mem_labels[mem_labels == new_idx_to_remove] = old_idx_to_restore
+    if sh is not None:
+        sh = sh.copy()
+        sh[sh == new_idx_to_remove] = old_idx_to_restore
+        _set_host_labels(mem_labels, sh)
     return mem_labels
 
 
 def _update_in_mem(old_values, new_values, old_labels, new_labels, old_idx, new_idx):
     """Overwrite the tokens labelled old_idx with those labelled new_idx (engine/inference.py:222-228)."""
+    osh, nsh = _host_labels(old_labels), _host_labels(new_labels)
+    if osh is not None and nsh is not None:
+        dst, src = _runs(osh == old_idx), _runs(nsh == new_idx)
+        if len(dst) == 1 and len(src) == 1 and dst[0][1] - dst[0][0] == src[0][1] - src[0][0]:
+            (a, b), (c, d) = dst[0], src[0]
+            for k in range(len(old_values)):
+                old_values[k][:, a:b] = new_values[k][:, c:d]
+            return old_values
     dst, src = old_labels == old_idx, new_labels == new_idx
     for k in range(len(old_values)):
         old_values[k][dst] = new_values[k][src]
     return old_values
+
+
+def _compact_storage(mem):
+    """Memory tensors handed back to the caller own exactly their rows (a prefix view would drag the evicted frames'
+    storage along, e.g. into a pickle, slam/model.py:431-440)."""
+    vals = [v.clone() if v.untyped_storage().nbytes() > v.numel() * v.element_size() else v for v in mem[0]]
+    lab = mem[1]
+    if lab.untyped_storage().nbytes() > lab.numel() * lab.element_size():
+        lab = _set_host_labels(lab.clone(), getattr(lab, "_m3r_labels_host", None))
+    return [vals, lab] + list(mem[2:])
 
 
 def _fresh_labels(new_mem, n_before, mem_before=None, n_new_views=None):
@@ -305,7 +389,7 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
                                                     viser_server=viser_server)
             res = unstack_pointmaps(idx_st, res)
             first_pass[lo:hi] = res
-            mem = list(new_mem)
+            mem = list(_shadow_after_call(mem_prev, new_mem, idx_st, x_st))
             new_labels = _fresh_labels(mem, n_before, mem_prev, hi - lo)
             if custom_callbacks:
                 _sync_host_copies()        # user callbacks may read the (host) results
@@ -348,7 +432,7 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
             if gone not in keyframes:
                 mem[0], mem[1] = _remove_from_mem(mem[0], mem[1], label_of[gone])
     _sync_host_copies()
-    return (mem, first_pass) if return_mem else first_pass
+    return (_compact_storage(mem), first_pass) if return_mem else first_pass
 
 
 # --------------------------------------------------------------------------------------------- offline keyframes + render
@@ -381,15 +465,14 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
                                                         post_process_function=post_process_function, device=device,
                                                         viser_server=viser_server)
                 new_labels = _fresh_labels(new_mem, get_Nmem(mem), mem, hi - lo)
+                new_mem = _shadow_after_call(mem, new_mem, idx_st, x_st)
                 if refresh:
                     assert mem is not None
                     for j, vid in enumerate(ids_i):
                         old = label_of[int(vid)]
                         if old == 0:
                             continue                                  # reference image: left as is
-                        dst, src = mem[1] == old, new_mem[1] == new_labels[j]
-                        for k in range(len(mem[0])):
-                            mem[0][k][dst] = new_mem[0][k][src]
+                        _update_in_mem(mem[0], new_mem[0], mem[1], new_mem[1], old, new_labels[j])
                     del new_mem
                 else:
                     mem = new_mem

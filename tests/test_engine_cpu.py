@@ -58,6 +58,50 @@ def test_inference_video_rolling_window():
     _check_mem(g, "video.mem", mem)
 
 
+def test_host_label_shadow_equals_device_masks(monkeypatch):
+    """The slice-based memory edits (host label shadow: no device sync, zero-copy tail eviction) must give exactly what the
+    reference's boolean-mask edits give: streaming schedule with eviction, refinement passes and two aspect ratios."""
+    import importlib
+    inf = importlib.import_module("must3r_b200.engine.inference")      # (the package also exports a function `inference`)
+    enc, dec = tiny_oracle(7)
+    imgs, tss = _views()
+    kw = dict(post_process_function=orc.postprocess, device="cpu", return_mem=True, local_context_size=2,
+              num_refinements_iterations=1)
+    calls = {"slices": 0}
+    real_runs = inf._runs
+
+    def counting_runs(mask):
+        calls["slices"] += 1
+        return real_runs(mask)
+
+    monkeypatch.setattr(inf, "_runs", counting_runs)
+    mem_a, pm_a = engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], **kw)
+    assert calls["slices"] > 0                                        # the shadow path really ran
+    sh = inf._host_labels(mem_a[1])
+    assert sh is not None and np.array_equal(sh, mem_a[1][0].numpy())  # shadow == device labels at the end
+    assert all(v.untyped_storage().nbytes() == v.numel() * v.element_size() for v in mem_a[0])   # compact storage
+    monkeypatch.setattr(inf, "_shadow_after_call", lambda mem_before, new_mem, idx_st, x_st: new_mem)
+    mem_b, pm_b = engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], **kw)
+    assert inf._host_labels(mem_b[1]) is None
+    assert torch.equal(mem_a[1], mem_b[1]) and [int(v) for v in mem_a[2:]] == [int(v) for v in mem_b[2:]]
+    for va, vb in zip(mem_a[0], mem_b[0]):
+        assert torch.equal(va, vb)
+    for da, db in zip(pm_a, pm_b):
+        for k in da:
+            assert torch.equal(da[k], db[k])
+    # offline keyframes + refinement (inference_multi_ar refresh path)
+    ids = [torch.tensor(i) for i in range(6)]
+    kw2 = dict(max_bs=2, post_process_function=orc.postprocess, device="cpu", return_mem=True, num_refinements_iterations=2)
+    mem_d, _, pm_d = engine.inference_multi_ar(enc, dec, imgs, ids, tss, [2, 1, 1], **kw2)
+    monkeypatch.undo()
+    mem_c, _, pm_c = engine.inference_multi_ar(enc, dec, imgs, ids, tss, [2, 1, 1], **kw2)
+    for va, vb in zip(mem_c[0], mem_d[0]):
+        assert torch.equal(va, vb)
+    for da, db in zip(pm_c, pm_d):
+        for k in da:
+            assert torch.equal(da[k], db[k])
+
+
 def test_inference_tensor_path_chunked_render():
     g = load_golden("engine.npz")
     enc, dec = tiny_oracle(7)
