@@ -309,6 +309,8 @@ def main():
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "traffic": NCU_TRAFFIC.get(dom, {}).get("bytes"), "traffic_of": NCU_TRAFFIC.get(dom, {}).get("launch"),
                 "peak_source": peak_src,
+                "note": "gemm_kernel<64> = the M=768 GEMMs of the one-view update chain: bounded by the per-SM L2->smem ingest "
+                        "(~70 B/clk/SM measured in-kernel, DESIGN.md section 7), not by the tensor pipe; per_kernel lists every category",
                 "per_kernel": {c: {"ms": round(p["ms"], 3), "launches": p["launches"],
                                    "tflops": round(p["flops"] / (p["ms"] * 1e-3) / 1e12, 1) if p["ms"] > 0 and p["flops"] else None,
                                    "frac": round(p["flops"] / (p["ms"] * 1e-3) / 1e12 / peak, 4) if p["ms"] > 0 and p["flops"] else None}
