@@ -227,14 +227,18 @@ def inference_multi_ar_batch(encoder, decoder, imgs, true_shape, mem=None, verbo
 # non-keyframe step of the streaming schedule does - is a zero-copy prefix view.  Without a shadow (a memory of unknown
 # provenance, or scenes with different label rows) the reference's device path runs.
 def _host_labels(mem_labels):
+    """-> numpy int64 row of the labels, or None.  (Kept on the tensor as a CPU torch tensor: that survives pickling and
+    `torch.load(weights_only=True)` of a saved memory, slam/model.py:431-440; a numpy attribute would not.)"""
     sh = getattr(mem_labels, "_m3r_labels_host", None)
     if sh is None or mem_labels.dim() != 2 or mem_labels.shape[0] != 1 or sh.shape[0] != mem_labels.shape[1]:
         return None
-    return sh
+    return sh.numpy()
 
 
 def _set_host_labels(mem_labels, shadow):
     try:
+        if shadow is not None and not torch.is_tensor(shadow):
+            shadow = torch.from_numpy(np.ascontiguousarray(shadow, dtype=np.int64))
         mem_labels._m3r_labels_host = shadow
     except Exception:  # noqa: BLE001  (tensor subclasses that refuse attributes)
         pass

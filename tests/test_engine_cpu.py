@@ -80,6 +80,12 @@ def test_host_label_shadow_equals_device_masks(monkeypatch):
     sh = inf._host_labels(mem_a[1])
     assert sh is not None and np.array_equal(sh, mem_a[1][0].numpy())  # shadow == device labels at the end
     assert all(v.untyped_storage().nbytes() == v.numel() * v.element_size() for v in mem_a[0])   # compact storage
+    import io
+    buf = io.BytesIO()
+    torch.save(tuple(mem_a), buf)                                     # a saved memory loads with the default (weights_only) loader
+    buf.seek(0)
+    back = torch.load(buf)
+    assert torch.equal(back[1], mem_a[1]) and np.array_equal(inf._host_labels(back[1]), sh)
     monkeypatch.setattr(inf, "_shadow_after_call", lambda mem_before, new_mem, idx_st, x_st: new_mem)
     mem_b, pm_b = engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], **kw)
     assert inf._host_labels(mem_b[1]) is None
