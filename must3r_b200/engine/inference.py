@@ -5,7 +5,8 @@ Same entry points, argument meaning and observable results: ``postprocess``, ``s
 ``inference_encoder``, ``inference``, ``get_Nmem``, ``unstack_pointmaps``, ``concat_preds``.  The functions
 are model-agnostic (they only call ``encoder(imgs, true_shape)`` / ``decoder(x, pos, true_shape, mem,
 render=...)``), so the CPU test-suite drives them with the oracle model and the GPU suite with the CUDA
-model.  ``compute_cam=True`` (Weiszfeld focal + Procrustes) is outside the hot path.
+model.  ``compute_cam=True`` (Weiszfeld focal + weighted Procrustes) is outside the hot path and
+runs as a few torch ops (``engine/camera.py``).
 """
 from __future__ import annotations
 
@@ -18,6 +19,7 @@ import numpy as np
 import torch
 
 from ..model.common import ActivationType
+from .camera import camera_from_pointmaps
 
 
 # --------------------------------------------------------------------------------------------- host copies
@@ -89,21 +91,23 @@ def _act(xyz, activation):
 def postprocess(pointmaps, pointmaps_activation=ActivationType.NORM_EXP, compute_cam=False):
     """engine/inference.py:16-48.  7-channel CUDA pointmaps with the NORM_EXP activation take the fused
     kernel (m3r_postprocess); everything else is evaluated with torch in fp32, like the reference."""
-    if compute_cam:
-        raise NotImplementedError("postprocess(compute_cam=True) needs roma + Weiszfeld focal estimation; "
-                                  "it is outside the must3r_b200 hot path (SURVEY.md §8f)")
     pm = pointmaps.float()
     act_name = getattr(pointmaps_activation, "value", pointmaps_activation)
     if pm.is_cuda and pm.shape[-1] == 7 and act_name == "norm_exp":
         from .. import ops
         pts, loc, conf = ops.postprocess_raw(pm)
-        return {"pts3d": pts, "pts3d_local": loc, "conf": conf}
+        out = {"pts3d": pts, "pts3d_local": loc, "conf": conf}
+        return camera_from_pointmaps(out) if compute_cam else out
     out = {"pts3d": _act(pm[..., :3], pointmaps_activation)}
     ch = pm.shape[-1]
     if ch >= 6:
         out["pts3d_local"] = _act(pm[..., 3:6], pointmaps_activation)
     if ch in (4, 7):
         out["conf"] = 1.0 + pm[..., -1].exp()
+    if compute_cam:
+        if "pts3d_local" not in out or "conf" not in out:
+            raise KeyError("compute_cam needs pts3d_local and conf (7-channel pointmaps, engine/inference.py:29-41)")
+        camera_from_pointmaps(out)
     return out
 
 

@@ -399,6 +399,41 @@ def postprocess(pointmaps: Tensor, activation: str = "norm_exp") -> Dict[str, Te
     return out
 
 
+def focal_weiszfeld(pts3d_local: Tensor, pp_xy: Tuple[float, float], iters: int = 10):
+    """estimate_focal_knowing_depth(focal_mode='weiszfeld'), dust3r/dust3r/post_process.py:12-60, in float64 numpy.
+    pts3d_local [B,H,W,3]; pixel grid (x = column, y = row, dust3r/dust3r/utils/geometry.py:15-37) minus the principal
+    point; focal = argmin sum |pixel - f (x,y)/z| by 10 IRLS steps from the L2 closed form."""
+    import numpy as np
+    p = pts3d_local.double().numpy()
+    B, H, W, _ = p.shape
+    gx, gy = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64), indexing="xy")
+    px = np.stack([gx - pp_xy[0], gy - pp_xy[1]], -1).reshape(1, H * W, 2)
+    p = p.reshape(B, H * W, 3)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ray = p[..., :2] / p[..., 2:3]
+    ray = np.nan_to_num(ray, nan=0.0, posinf=0.0, neginf=0.0)
+    num, den = (ray * px).sum(-1), (ray ** 2).sum(-1)
+    f = num.mean(1) / den.mean(1)
+    for _ in range(iters):
+        w = 1.0 / np.clip(np.linalg.norm(px - f[:, None, None] * ray, axis=-1), 1e-8, None)
+        f = (w * num).mean(1) / (w * den).mean(1)
+    return torch.from_numpy(np.clip(f, 0.0, None))
+
+
+def rigid_registration(x: Tensor, y: Tensor, w: Tensor):
+    """roma.rigid_points_registration(x, y, weights=w, compute_scaling=False) as used at must3r/engine/inference.py:38-41
+    (roma is a PyPI dependency of the reference, not vendored, version unpinned; its documented algorithm is the weighted
+    orthogonal Procrustes / Kabsch solution).  One problem: x, y [n,3], w [n] -> R [3,3] (det +1), t [3]; float64 numpy."""
+    import numpy as np
+    x, y, w = x.double().numpy(), y.double().numpy(), w.double().numpy()[:, None]
+    xc, yc = (w * x).sum(0) / w.sum(), (w * y).sum(0) / w.sum()
+    H = (w * (y - yc)).T @ (x - xc)
+    U, _, Vt = np.linalg.svd(H)
+    D = np.diag([1.0, 1.0, np.sign(np.linalg.det(U @ Vt))])
+    R = U @ D @ Vt
+    return torch.from_numpy(R), torch.from_numpy(yc - R @ xc)
+
+
 # --------------------------------------------------------------------------------------
 # callable wrappers with the reference's model API (so engine code can drive the oracle)
 # --------------------------------------------------------------------------------------

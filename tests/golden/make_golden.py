@@ -122,6 +122,23 @@ def tiny_model_golden():
     out["manyar.enc_x"], out["manyar.enc_pos"] = xm.numpy(), pm_.numpy()
     # postprocess (engine/inference.py:16-27)
     pp_out = ref_engine.postprocess(torch.from_numpy(out["kv.pm_render"]), ActivationType.NORM_EXP)
+    # focal of postprocess(compute_cam=True) (engine/inference.py:29-35); the pose half needs roma, which is not installed
+    from dust3r.post_process import estimate_focal_knowing_depth
+    loc = pp_out["pts3d_local"]
+    Hh, Ww = loc.shape[-3], loc.shape[-2]
+    out["kv.post.focal"] = estimate_focal_knowing_depth(loc.reshape(-1, Hh, Ww, 3), torch.tensor((Ww / 2, Hh / 2)),
+                                                         focal_mode="weiszfeld").numpy()
+    # the same estimator on noisy pinhole pointmaps with known focals (a non-degenerate known-answer case)
+    gen = torch.Generator().manual_seed(21)
+    f_true = torch.tensor([40.0, 55.0, 70.0])
+    vv, uu = torch.meshgrid(torch.arange(Hh, dtype=torch.float32), torch.arange(Ww, dtype=torch.float32), indexing="ij")
+    z = 2.0 + torch.rand(3, Hh, Ww, generator=gen) * 3.0
+    xl = (uu[None] - Ww / 2) * z / f_true.view(3, 1, 1)
+    yl = (vv[None] - Hh / 2) * z / f_true.view(3, 1, 1)
+    cam_pts = torch.stack([xl, yl, z], -1) + 0.01 * torch.randn(3, Hh, Ww, 3, generator=gen)
+    cam_pts[0, 0, 0, 2] = 0.0                                   # a zero depth: exercises the nan_to_num branch
+    out["cam.pts_local"] = cam_pts.numpy()
+    out["cam.focal"] = estimate_focal_knowing_depth(cam_pts, torch.tensor((Ww / 2, Hh / 2)), focal_mode="weiszfeld").numpy()
     for k, v in pp_out.items():
         out[f"kv.post.{k}"] = v.numpy()
     np.savez_compressed(os.path.join(HERE, "tiny_model.npz"), **out)

@@ -2,6 +2,7 @@
 against the reference engine's outputs (tests/golden/engine.npz), with the CPU oracle standing in as the model.
 fp32 vs fp32: 3e-5 rel-L2."""
 import numpy as np
+import pytest
 import torch
 
 from helpers import load_golden, tiny_oracle, rel
@@ -118,6 +119,36 @@ def test_inference_tensor_path_chunked_render():
     assert rel(pm, g["inference.pm_sel"]) < TOL
 
 
+def test_postprocess_compute_cam():
+    """postprocess(compute_cam=True) (engine/inference.py:29-47): focal against the reference's estimator output, pose against
+    the oracle's float64 Kabsch on the same points, and a synthetic scene whose camera is known."""
+    g = load_golden("tiny_model.npz")
+    from must3r_b200.engine import camera
+    f = camera.estimate_focal_weiszfeld(torch.from_numpy(g["cam.pts_local"]), torch.tensor((24.0, 16.0)))
+    assert np.allclose(f.numpy(), g["cam.focal"], rtol=1e-4)
+    pm = torch.from_numpy(g["kv.pm_render"])                          # [1, 5, 32, 48, 7]
+    out = engine.postprocess(pm, "norm_exp", compute_cam=True)
+    assert out["focal"].shape == (1, 5) and out["c2w"].shape == (1, 5, 4, 4)
+    assert np.allclose(out["focal"].numpy().ravel(), g["kv.post.focal"], rtol=2e-3, atol=1e-4)
+    for v in range(5):
+        R, t = orc.rigid_registration(out["pts3d_local"][0, v].reshape(-1, 3), out["pts3d"][0, v].reshape(-1, 3),
+                                      out["conf"][0, v].reshape(-1) - 1.0)
+        assert torch.allclose(out["c2w"][0, v, :3, :3].double(), R, atol=2e-4)
+        assert torch.allclose(out["c2w"][0, v, :3, 3].double(), t, atol=2e-4)
+        assert torch.equal(out["c2w"][0, v, 3], torch.tensor([0.0, 0.0, 0.0, 1.0]))
+    # known camera: world points = R0 * local + t0, focal 55
+    loc = torch.from_numpy(g["cam.pts_local"][1])
+    ang = 0.4
+    R0 = torch.tensor([[np.cos(ang), 0.0, np.sin(ang)], [0.0, 1.0, 0.0], [-np.sin(ang), 0.0, np.cos(ang)]], dtype=torch.float32)
+    t0 = torch.tensor([1.0, 2.0, -0.5])
+    res = camera.camera_from_pointmaps({"pts3d": (loc @ R0.T + t0)[None], "pts3d_local": loc[None],
+                                        "conf": 1.0 + torch.rand(1, 32, 48)})
+    assert abs(float(res["focal"][0]) - 55.0) < 0.1
+    assert torch.allclose(res["c2w"][0, :3, :3], R0, atol=1e-4) and torch.allclose(res["c2w"][0, :3, 3], t0, atol=1e-3)
+    with pytest.raises(KeyError):
+        engine.postprocess(pm[..., :3], "norm_exp", compute_cam=True)
+
+
 def test_stack_views_groups_and_none_handling():
     ts = torch.tensor([[32, 48], [48, 32], [32, 48], [32, 48], [48, 32]])
     vals = [torch.full((2,), float(i)) for i in range(5)]
@@ -131,14 +162,9 @@ def test_stack_views_groups_and_none_handling():
     assert idx == [[0, 3], [1, 4], [2]] and v[2] is None and v[0].shape[0] == 2
 
 
-def test_postprocess_cpu_matches_oracle_and_rejects_cam():
+def test_postprocess_cpu_matches_oracle():
     pm = torch.randn(2, 8, 8, 7)
     out = engine.postprocess(pm)
     ref = orc.postprocess(pm)
     for k in ref:
         assert torch.allclose(out[k], ref[k])
-    try:
-        engine.postprocess(pm, compute_cam=True)
-        assert False
-    except NotImplementedError:
-        pass

@@ -96,6 +96,37 @@ def test_postprocess():
         assert rel(out[k], g[f"kv.post.{k}"]) < 1e-6
 
 
+def test_focal_weiszfeld_vs_reference():
+    """Oracle restatement of estimate_focal_knowing_depth(focal_mode='weiszfeld') against the reference's own outputs:
+    noisy pinhole pointmaps with focals 40 / 55 / 70 px (incl. a zero depth) and the degenerate random-weight pointmaps."""
+    g = load_golden("tiny_model.npz")
+    f = orc.focal_weiszfeld(torch.from_numpy(g["cam.pts_local"]), (48 / 2, 32 / 2))
+    assert np.allclose(f.numpy(), g["cam.focal"], rtol=2e-5)
+    loc = torch.from_numpy(g["kv.post.pts3d_local"]).reshape(-1, 32, 48, 3)
+    f = orc.focal_weiszfeld(loc, (48 / 2, 32 / 2))
+    assert np.allclose(f.numpy(), g["kv.post.focal"], rtol=1e-3, atol=1e-5)
+
+
+def test_rigid_registration_known_answer():
+    """Weighted Kabsch restatement (roma.rigid_points_registration): recovers a known rotation + translation exactly from
+    noiseless points, ignores zero-weight outliers, and never returns a reflection."""
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(200, 3, generator=gen, dtype=torch.float64)
+    ang = 0.7
+    R0 = torch.tensor([[np.cos(ang), -np.sin(ang), 0.0], [np.sin(ang), np.cos(ang), 0.0], [0.0, 0.0, 1.0]], dtype=torch.float64)
+    R0 = R0 @ torch.tensor([[1.0, 0.0, 0.0], [0.0, np.cos(0.3), -np.sin(0.3)], [0.0, np.sin(0.3), np.cos(0.3)]], dtype=torch.float64)
+    t0 = torch.tensor([0.5, -1.0, 2.0], dtype=torch.float64)
+    y = x @ R0.T + t0
+    w = torch.rand(200, generator=gen, dtype=torch.float64) + 0.1
+    y[:10] += 5.0
+    w[:10] = 0.0                                                    # outliers with zero weight
+    R, t = orc.rigid_registration(x, y, w)
+    assert torch.allclose(R, R0, atol=1e-10) and torch.allclose(t, t0, atol=1e-10)
+    assert abs(float(torch.linalg.det(R)) - 1.0) < 1e-10
+    Rm, _ = orc.rigid_registration(x, x * torch.tensor([1.0, 1.0, -1.0], dtype=torch.float64), torch.ones(200, dtype=torch.float64))
+    assert float(torch.linalg.det(Rm)) > 0.999                       # mirrored target: still a proper rotation
+
+
 @pytest.mark.parametrize("tag,H,W,size", [("224", 224, 224, 224)])
 def test_full_size_digest(tag, H, W, size):
     """Full ViT-L / ViT-B architecture (24+12 layers) against reference digests."""
