@@ -201,6 +201,20 @@ def engine_golden():
         for k, v in d.items():
             out[f"multi_ar.pm.{i}.{k}"] = v.numpy()
     mem_arrays("multi_ar.mem", mem, out)
+    # render-only call on a precomputed memory, subset of the views (engine/inference.py:370-527: precomputed_mem, to_render)
+    _, pm_sel = ref_engine.inference_multi_ar(enc, dec, imgs, img_ids, tss, [2, 1, 1], max_bs=None, to_render=[5, 0, 2],
+                                              precomputed_mem=mem, post_process_function=pp, device="cpu")
+    for i, d in enumerate(pm_sel):
+        for k, v in d.items():
+            out[f"multi_ar.pm_sel.{i}.{k}"] = v.numpy()
+    # video with one refinement pass (keyframe refresh + between-pass eviction), window of 3
+    mem, pm0 = ref_engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], max_bs=None,
+                                                  post_process_function=pp, device="cpu", return_mem=True,
+                                                  local_context_size=3, num_refinements_iterations=1)
+    for i, d in enumerate(pm0):
+        for k, v in d.items():
+            out[f"video_ref.pm0.{i}.{k}"] = v.numpy()
+    mem_arrays("video_ref.mem", mem, out)
     # video: rolling window of 2, keyframe iff id % 3 == 0 (engine/inference.py:236)
     mem, pm0 = ref_engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], max_bs=None,
                                                   post_process_function=pp, device="cpu", return_mem=True,

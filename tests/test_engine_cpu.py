@@ -47,6 +47,47 @@ def test_inference_multi_ar_with_refinement():
     _check_mem(g, "multi_ar.mem", mem)
 
 
+def test_inference_multi_ar_precomputed_mem_and_to_render():
+    """Render-only call on a memory built earlier, for a subset of the views in a caller-chosen order."""
+    g = load_golden("engine.npz")
+    enc, dec = tiny_oracle(7)
+    imgs, tss = _views()
+    ids = [torch.tensor(i) for i in range(6)]
+    mem, _, _ = engine.inference_multi_ar(enc, dec, imgs, ids, tss, [2, 1, 1], max_bs=2,
+                                          post_process_function=orc.postprocess, device="cpu", return_mem=True,
+                                          num_refinements_iterations=1)
+    first, pm = engine.inference_multi_ar(enc, dec, imgs, ids, tss, [2, 1, 1], to_render=[5, 0, 2], precomputed_mem=mem,
+                                          post_process_function=orc.postprocess, device="cpu")
+    assert first is None and len(pm) == 3
+    for i, d in enumerate(pm):
+        for k, v in d.items():
+            assert rel(v, g[f"multi_ar.pm_sel.{i}.{k}"]) < TOL, (i, k)
+
+
+def test_inference_video_with_refinement_pass():
+    """Streaming schedule with a second pass: keyframes are refreshed in place, non-keyframes evicted between passes."""
+    g = load_golden("engine.npz")
+    enc, dec = tiny_oracle(7)
+    imgs, tss = _views()
+    mem, pm0 = engine.inference_video_multi_ar(enc, dec, imgs, tss, [2, 1, 1, 1, 1], post_process_function=orc.postprocess,
+                                               device="cpu", return_mem=True, local_context_size=3,
+                                               num_refinements_iterations=1)
+    for i, d in enumerate(pm0):
+        for k, v in d.items():
+            assert rel(v, g[f"video_ref.pm0.{i}.{k}"]) < TOL, (i, k)
+    _check_mem(g, "video_ref.mem", mem)
+
+
+def test_concat_preds_and_groupby_consecutive():
+    a = {"pts3d": torch.zeros(2, 1, 4, 4, 3), "conf": torch.ones(2, 1, 4, 4)}
+    b = {"pts3d": torch.ones(2, 3, 4, 4, 3), "conf": torch.zeros(2, 3, 4, 4), "extra": torch.zeros(1)}
+    out = engine.concat_preds(a, b)                                  # engine/inference.py:691-695: cat along the view axis
+    assert out["pts3d"].shape == (2, 4, 4, 4, 3) and out["conf"].shape == (2, 4, 4, 4) and out["extra"].shape == (1,)
+    assert float(out["pts3d"][:, 0].abs().sum()) == 0 and float(out["pts3d"][:, 1:].min()) == 1
+    assert engine.groupby_consecutive([5, 1, 2, 3, 9, 8]) == [(1, 3), (5, 5), (8, 9)]
+    assert engine.groupby_consecutive([]) == []
+
+
 def test_inference_video_rolling_window():
     g = load_golden("engine.npz")
     enc, dec = tiny_oracle(7)
