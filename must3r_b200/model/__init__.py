@@ -26,72 +26,62 @@ def apply_activation(xyz, activation):
 
 
 def get_pointmaps_activation(decoder, verbose=True):
-    """must3r/model/__init__.py:8-15"""
-    try:
-        pointmaps_activation = decoder.pointmaps_activation
-    except Exception:
-        pointmaps_activation = ActivationType.NORM_EXP
+    """Activation the decoder's pointmaps expect; NORM_EXP for decoders that do not say (must3r/model/__init__.py:8-15)."""
+    act = getattr(decoder, "pointmaps_activation", ActivationType.NORM_EXP)
     if verbose:
-        print(f'pointmaps_activation set to {pointmaps_activation}')
-    return pointmaps_activation
+        print(f"pointmaps_activation set to {act}")
+    return act
+
+
+_AMP_DTYPES = {"fp16": torch.float16, "bf16": torch.bfloat16}
 
 
 def get_dtype(amp):
-    """must3r/model/__init__.py:18-27"""
-    if amp == "fp16":
-        return torch.float16
-    elif amp == "bf16":
-        return torch.bfloat16
+    """'fp16' / 'bf16' / falsy -> torch dtype (must3r/model/__init__.py:18-27)."""
+    if amp in _AMP_DTYPES:
+        return _AMP_DTYPES[amp]
     assert not amp
     return torch.float32
 
 
 def convert_decoder_args(decoder_args):
-    """must3r/model/__init__.py:53-63: CausalMUSt3R -> MUSt3R, landscape_only -> False"""
-    decoder_args = decoder_args.replace(' ', '')
-    for k, v in {'CausalMUSt3R': 'MUSt3R', 'landscape_only=True': "landscape_only=False"}.items():
-        decoder_args = decoder_args.replace(k, v)
-    if 'landscape_only=False' not in decoder_args:
-        decoder_args = decoder_args[:-1] + ",landscape_only=False)"
-    return decoder_args
+    """Constructor string of a training checkpoint -> inference decoder (must3r/model/__init__.py:53-63): the causal training
+    class becomes MUSt3R and the head is told not to assume landscape inputs."""
+    text = "".join(decoder_args.split(" "))
+    text = text.replace("CausalMUSt3R", "MUSt3R").replace("landscape_only=True", "landscape_only=False")
+    if "landscape_only=False" in text:
+        return text
+    return f"{text[:-1]},landscape_only=False)"
+
+
+_IMG_SIZE_RE = re.compile(r"img_size=\((\d+),(\d+)\)")
+_POS_EMBED_RE = re.compile(r"pos_embed='([A-Za-z]+)(\d+)(?:_(\d+):(\d+))?'")
 
 
 def set_image_size_in_args(model_args, img_size, verbose=True):
-    """must3r/model/__init__.py:66-108: rewrite img_size and the adaptive RoPE name ('RoPE100_512:768')."""
-    model_args = model_args.replace(' ', '')
-    match_size = re.search(r'img_size=\((\d+),(\d+)\)', model_args)
-    if not match_size:
+    """Point a constructor string at another (square) img_size and rename the adaptive RoPE accordingly
+    (must3r/model/__init__.py:66-108): 'RoPE100' trained at 512 and run at 768 becomes 'RoPE100_512:768'; an existing
+    '<name><freq>_<base>:<cur>' keeps its base; a string without pos_embed gets one appended."""
+    text = "".join(model_args.split(" "))
+    size = _IMG_SIZE_RE.search(text)
+    if size is None:
         raise ValueError("No image_size tuple found in model args")
-    h, w = map(int, match_size.groups())
-    assert h == w
+    side, other = (int(v) for v in size.groups())
+    assert side == other
+    rope = _POS_EMBED_RE.search(text)
+    name, freq = (rope.group(1), int(rope.group(2))) if rope else ("RoPE", 100)
+    adaptive = rope is not None and rope.group(3) is not None
+    base, current = (int(rope.group(3)), int(rope.group(4))) if adaptive else (side, side)
     if verbose:
-        print(f"image_size {h} -> {img_size}")
-    m = re.search(r"pos_embed='([A-Za-z]+)(\d+)\_(\d+):(\d+)'", model_args)
-    if m:
-        prefix, freq, base_size, new_size = m.groups()
-        freq, base_size, new_size = int(freq), int(base_size), int(new_size)
-        pos_embed_is_arg = True
-    else:
-        m = re.search(r"pos_embed='([A-Za-z]+)(\d+)'", model_args)
-        if m:
-            prefix, freq = m.groups()
-            freq = int(freq)
-            pos_embed_is_arg = True
-        else:
-            prefix, freq = "RoPE", 100
-            pos_embed_is_arg = False
-        base_size = new_size = h
-    if verbose:
-        print(f"Parsed pos_embed: {prefix}{freq}, base size = {base_size}")
-    if img_size != h:
-        model_args = model_args.replace(f'img_size=({h},{h})', f'img_size=({img_size},{img_size})')
-    if img_size != new_size:
-        new_pos_embed = f"{prefix}{freq}_{base_size}:{img_size}"
-        if pos_embed_is_arg:
-            model_args = re.sub(r"(pos_embed=')(?:[A-Za-z]+\d+(?:_\d+:\d+)?)(')", rf"\1{new_pos_embed}\2", model_args)
-        else:
-            model_args = model_args[:-1] + ",pos_embed='" + new_pos_embed + "')"
-    return model_args
+        print(f"image_size {side} -> {img_size}; pos_embed {name}{freq} (base size {base})")
+    if img_size != side:
+        text = text.replace(f"img_size=({side},{side})", f"img_size=({img_size},{img_size})")
+    if img_size == current:
+        return text
+    renamed = f"pos_embed='{name}{freq}_{base}:{img_size}'"
+    if rope is None:
+        return f"{text[:-1]},{renamed})"
+    return text[:rope.start()] + renamed + text[rope.end():]
 
 
 def load_model(chkpt_path, encoder=None, decoder=None, device='cuda', img_size=None, memory_mode=None, verbose=True):

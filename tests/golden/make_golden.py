@@ -234,8 +234,27 @@ def engine_golden():
     print("engine.npz", len(out), "arrays")
 
 
+def model_args_golden():
+    """Constructor-string rewrites of load_model (must3r/model/__init__.py:53-108) -> tests/golden/model_args.json."""
+    import json
+    import must3r.model as ref_model
+    encs = ["Dust3rEncoder(img_size=(512, 512), patch_embed='PatchEmbedDust3R')", "Dust3rEncoder(img_size=(224,224))",
+            "Dust3rEncoder(img_size=(512,512),pos_embed='RoPE100')", "Dust3rEncoder(img_size=(512,512),pos_embed='RoPE100_224:512')",
+            "MUSt3R(img_size=(512, 512), feedback_type='single_mlp', memory_mode=\"kv\", pos_embed='RoPE200_512:768', landscape_only=True)",
+            "CausalMUSt3R(img_size=(224, 224), pos_embed='RoPE100', mem_dropout=0.1)"]
+    decs = ["CausalMUSt3R(img_size=(512, 512), feedback_type='single_mlp', memory_mode=\"kv\", mem_dropout=0.1, "
+            "dropout_mode='temporary', use_xformers_mask=True, use_mem_mask=True)",
+            "MUSt3R(img_size=(512,512),landscape_only=True)", "MUSt3R(img_size=(512,512), landscape_only=False, head='Linear')"]
+    out = {"set_image_size": [[e, sz, ref_model.set_image_size_in_args(e, sz, verbose=False)] for e in encs for sz in (224, 512, 768)],
+           "convert": [[d, ref_model.convert_decoder_args(d)] for d in decs]}
+    json.dump(out, open(os.path.join(HERE, "model_args.json"), "w"), indent=1)
+    print("model_args.json", len(out["set_image_size"]) + len(out["convert"]), "cases")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tiny", "engine", "full"]
+    which = sys.argv[1:] or ["tiny", "engine", "full", "args"]
+    if "args" in which:
+        model_args_golden()
     if "tiny" in which:
         tiny_model_golden()
     if "engine" in which:

@@ -87,3 +87,19 @@ def test_state_dict_keys_are_the_references():
     assert float(dec.feedback_layer.fc2.weight.abs().sum()) > 0
     fresh = MUSt3R(feedback_type="single_mlp")
     assert float(fresh.feedback_layer.fc2.weight.abs().sum()) == 0      # feedback_mechanism.py:26-35
+
+
+def test_constructor_string_rewrites_match_reference():
+    """set_image_size_in_args / convert_decoder_args (must3r/model/__init__.py:53-108) against strings produced by the
+    reference's own functions (tests/golden/model_args.json, generated in the build container)."""
+    import json
+    from must3r_b200.model import set_image_size_in_args, convert_decoder_args, get_dtype
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "model_args.json")))
+    for args, size, want in g["set_image_size"]:
+        assert set_image_size_in_args(args, size, verbose=False) == want, (args, size)
+    for args, want in g["convert"]:
+        assert convert_decoder_args(args) == want, args
+    with pytest.raises(ValueError):
+        set_image_size_in_args("MUSt3R()", 224, verbose=False)
+    assert get_dtype("fp16") == torch.float16 and get_dtype("bf16") == torch.bfloat16 and get_dtype(None) == torch.float32
+
