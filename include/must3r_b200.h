@@ -19,8 +19,9 @@
 extern "C" {
 #endif
 
-#define M3R_ABI_VERSION 3
+#define M3R_ABI_VERSION 4
 #define M3R_MAX_PEERS 8
+#define M3R_MAX_GROUPS 16
 
 /* m3r_decoder_call.mem_mode (MEMORY_MODES, must3r/model/blocks/layers.py:9) */
 #define M3R_MEM_KV 0
@@ -88,9 +89,33 @@ typedef struct {
    * its first weight tiles before the programmatic-dependency wait, hiding their HBM latency behind the predecessor's
    * tail.  0 = no assumption. */
   int32_t w_static;
+  /* LayerNorm fused into the PRODUCING GEMM (must3r/model/blocks/layers.py:42,46,65,70,71,76 call sites): when norm_out
+   * != NULL the output must be the fp32 residual stream x [M,N] with N = the model width (N % 64 == 0, N <= 768) and the
+   * epilogue also writes normalised rows (x - mean) * rsqrt(var + norm_eps) as 16-bit to norm_out (leading dim ldn): the
+   * A operand of the next GEMM, whose weight / bias carry the LayerNorm affine (W * diag(gamma), b + W beta).  The CTAs
+   * holding the column tiles of one 128-row block exchange per-row (mean, M2) partials through device memory and meet
+   * at a device-scope counter, so the whole problem must fit in one wave (ceil(M/128) * N/64 <= SM count) and such
+   * launches must not run concurrently on two streams of one device. */
+  void* norm_out;
+  int64_t ldn;
+  float norm_eps;
 } m3r_gemm_args;
 
 int m3r_gemm(const m3r_gemm_args* args, void* stream);
+
+/* Grouped form: `groups` problems of identical shape [args->M, args->N, args->K] in one launch.  A = [groups*M, K]
+ * (group g = rows [g*M, (g+1)*M)), W rows [g*w_group_rows, +N), bias + g*bias_group; args->out / peer_out are ignored,
+ * group g writes out[g] (and peer_out[g*M3R_MAX_PEERS + r], r < args->n_peer_out) with args' ldc / row remap.
+ * Replaces the per-level K|V projections of the memory append (must3r/model/decoder.py:323-330). */
+typedef struct {
+  int32_t groups;
+  int64_t w_group_rows;
+  int64_t bias_group;
+  void* out[M3R_MAX_GROUPS];
+  void* peer_out[M3R_MAX_GROUPS * M3R_MAX_PEERS];
+} m3r_gemm_group;
+
+int m3r_gemm_grouped(const m3r_gemm_args* args, const m3r_gemm_group* grp, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * LayerNorm over the last dim of fp32 rows (optionally of x + add), output 16-bit (GEMM operand) or fp32.
@@ -101,6 +126,14 @@ int m3r_gemm(const m3r_gemm_args* args, void* stream);
 int m3r_layernorm(const float* x, int64_t ldx, const float* add, int64_t ldadd, const float* gamma,
                   const float* beta, float eps, int32_t M, int32_t D, void* out, int64_t ldo, int32_t out_dtype,
                   int32_t is_bf16, void* stream);
+
+/* Affine-free LayerNorm: out16 = ((x [+ add]) - mean) * rsqrt(var + eps) as 16-bit rows = the A operand of a GEMM whose
+ * weights carry the LayerNorm affine (W * diag(gamma), b + W beta).  `add` (may be NULL) is applied to rows < add_rows and
+ * repeats with period add_period rows: one launch normalises new_mem[l] + offset of every decoder level
+ * (must3r/model/feedback_mechanism.py:49-51, decoder.py:323-330).  Used where the producing GEMM cannot emit the
+ * normalised rows itself (m3r_gemm_args.norm_out: multi-wave problems). */
+int m3r_normalize16(const float* x, int64_t ldx, const float* add, int64_t ldadd, int32_t add_rows, int32_t add_period,
+                    float eps, int32_t M, int32_t D, void* out16, int64_t ldo, int32_t is_bf16, void* stream);
 
 /* fp32 -> 16-bit cast of [M,D] rows (encoder features entering the decoder projector, decoder.py:274). */
 int m3r_cast16(const float* x, int64_t ldx, int32_t M, int32_t D, void* out, int64_t ldo, int32_t is_bf16,
@@ -201,20 +234,24 @@ int64_t m3r_encoder_workspace_bytes(const m3r_encoder_weights* w, int32_t V, int
 int m3r_encoder_forward(const m3r_encoder_weights* w, const float* img, int32_t V, int32_t H, int32_t W,
                         const int64_t* pos, float* out_x, void* workspace, int64_t workspace_bytes, void* stream);
 
-/* CachedDecoderBlock (must3r/model/blocks/layers.py:57-99), memory_mode 'kv':
- * kv_w / kv_b = cat(cross_attn.projk, cross_attn.projv) so one GEMM emits the stored K|V row. */
+/* CachedDecoderBlock (must3r/model/blocks/layers.py:57-99).  Every LayerNorm of the block is applied WITHOUT its affine
+ * (by the epilogue of the GEMM that produced the rows, m3r_gemm_args.norm_out, or by m3r_normalize16); the affine lives in the
+ * consuming Linear: W' = W * diag(gamma), b' = b + W beta (exact in real arithmetic; rounded to 16 bits once, like W).
+ * Because norm1 and norm_y normalise the same block input, the self-attention qkv projection and the K|V projection of
+ * the new memory tokens (layers.py:81-88,91) become ONE GEMM with the stacked weight a_w. */
 typedef struct {
-  const float* norm1_w; const float* norm1_b;
-  const void* qkv_w; const float* qkv_b;       /* [3D,D] */
-  const void* proj_w; const float* proj_b;     /* [D,D]  */
-  const float* norm2_w; const float* norm2_b;
-  const float* normy_w; const float* normy_b;
-  const void* q_w; const float* q_b;           /* cross_attn.projq [D,D] */
-  const void* kv_w; const float* kv_b;         /* [2D,D] */
+  const void* a_w; const float* a_b;           /* [5D,D]: rows [0,3D) attn.qkv (norm1 folded), rows [3D,5D) cross_attn.projk ;
+                                                  projv (norm_y folded).  blocks[l].a_w == blocks[0].a_w + l*5D*D and
+                                                  blocks[l].a_b == blocks[0].a_b + l*5D let the memory append run as one
+                                                  grouped GEMM; otherwise it falls back to one GEMM per level */
+  const void* proj_w; const float* proj_b;     /* attn.proj [D,D] */
+  const void* q_w; const float* q_b;           /* cross_attn.projq [D,D], norm2 folded */
   const void* cproj_w; const float* cproj_b;   /* cross_attn.proj [D,D] */
-  const float* norm3_w; const float* norm3_b;
-  const void* fc1_w; const float* fc1_b;
-  const void* fc2_w; const float* fc2_b;
+  const void* fc1_w; const float* fc1_b;       /* mlp.fc1 [4D,D], norm3 folded */
+  const void* fc2_w; const float* fc2_b;       /* mlp.fc2 [D,4D] */
+  const float* normy_w; const float* normy_b;  /* norm_y affine: memory_mode norm_y / raw only (rows stored / normalised at use) */
+  const void* kv_w; const float* kv_b;         /* UNFOLDED [projk ; projv] [2D,D]: memory_mode norm_y / raw (K|V of stored rows
+                                                  projected at use, layers.py:92-96); may be NULL for memory_mode kv */
 } m3r_dec_block;
 
 /* MUSt3R (must3r/model/decoder.py:14-156) */
@@ -226,11 +263,9 @@ typedef struct {
   const void* embed_w; const float* embed_b;   /* feat_embed_enc_to_dec [D,enc_dim] */
   const float* image2_embed;                   /* [D] */
   const m3r_dec_block* blocks;                 /* host array [depth] */
-  const float* fbn_w; const float* fbn_b;      /* feedback_norm */
-  const void* fb1_w; const float* fb1_b;       /* feedback_layer.fc1 [4D,D] (or the single linear [D,D]) */
+  const void* fb1_w; const float* fb1_b;       /* feedback_layer.fc1 [4D,D] (or the single linear [D,D]), feedback_norm folded */
   const void* fb2_w; const float* fb2_b;       /* feedback_layer.fc2 [D,4D] */
-  const float* normd_w; const float* normd_b;  /* norm_dec */
-  const void* head_w; const float* head_b;     /* head_dec.proj [out_dim,D] */
+  const void* head_w; const float* head_b;     /* head_dec.proj [out_dim,D], norm_dec folded */
 } m3r_decoder_weights;
 
 /* One aspect-ratio group of a decoder call (MUSt3R.forward_list, decoder.py:158): B scenes x n_views views */
@@ -276,6 +311,14 @@ int m3r_peer_free(void* ptr);
 int m3r_ipc_export(void* ptr, void* handle64);
 int m3r_ipc_open(const void* handle64, void** ptr);
 int m3r_ipc_close(void* ptr);
+/* Device-side barrier of the multi-GPU schedule (no reference counterpart; replaces a host-blocking collective per update
+ * round).  Each rank owns slot `rank` of a uint32[world] flag array that lives in every rank's peer-visible memory.
+ * m3r_peer_signal(flag_slots = address of MY slot in each of the n ranks' arrays, value): enqueued after the kernels whose
+ * peer stores must be visible; writes `value` (a monotonically increasing epoch) with system-scope release semantics.
+ * m3r_peer_wait(local_flags = this rank's own array, rank_mask, value): a kernel that spins on the GPU until every slot r
+ * with bit r of rank_mask set has reached `value`; work enqueued after it sees the rows those ranks stored. */
+int m3r_peer_signal(void* const* flag_slots, int32_t n, uint32_t value, void* stream);
+int m3r_peer_wait(const void* local_flags, uint32_t rank_mask, uint32_t value, void* stream);
 
 /* MUSt3R.forward / forward_list (decoder.py:158-350) for memory_mode 'kv'. */
 int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decoder_call* call, void* workspace,

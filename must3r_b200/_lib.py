@@ -30,7 +30,13 @@ class GemmArgs(C.Structure):
         ("n_peer_out", C.c_int32),
         ("peer_out", C.c_void_p * 8),
         ("w_static", C.c_int32),
+        ("norm_out", C.c_void_p), ("ldn", C.c_int64), ("norm_eps", C.c_float),
     ]
+
+
+class GemmGroup(C.Structure):
+    _fields_ = [("groups", C.c_int32), ("w_group_rows", C.c_int64), ("bias_group", C.c_int64),
+                ("out", C.c_void_p * 16), ("peer_out", C.c_void_p * (16 * 8))]
 
 
 class AttnArgs(C.Structure):
@@ -56,6 +62,9 @@ SIGNATURES = {
     "m3r_prof_enable": (None, [C.c_int]),
     "m3r_prof_read": (C.c_int, [C.POINTER(C.c_double)]),
     "m3r_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "m3r_gemm_grouped": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(GemmGroup), C.c_void_p]),
+    "m3r_normalize16": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32,
+                                  C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "m3r_layernorm": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float,
                                 C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "m3r_cast16": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
@@ -75,6 +84,8 @@ SIGNATURES = {
     "m3r_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "m3r_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "m3r_ipc_close": (C.c_int, [C.c_void_p]),
+    "m3r_peer_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_uint32, C.c_void_p]),
+    "m3r_peer_wait": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
 }
 
 

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libm3r_b200.so")
 SOURCES = ["runtime.cu", "elementwise.cu", "gemm.cu", "attention.cu", "model.cu"]  # missing files are skipped
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math_off_placeholder"]
+              "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:
@@ -33,7 +33,7 @@ def _stale(target: str, deps) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    flags = [f for f in NVCC_FLAGS if f != "--use_fast_math_off_placeholder"]
+    flags = list(NVCC_FLAGS)
     variant = "trace" if os.environ.get("M3R_TRACE") == "1" else "release"
     if variant == "trace":                               # debug build: in-kernel %globaltimer stamps (tools/trace_*.py)
         flags.append("-DM3R_TRACE")

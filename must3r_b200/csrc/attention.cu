@@ -127,8 +127,8 @@ __device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) { uint64_t d; a
 // 2^x for a pair on the FMA/ALU pipes instead of the MUFU: Cody-Waite split x = n + f (round to nearest via the
 // 1.5*2^23 magic add), degree-3 minimax polynomial for 2^f on [-0.5,0.5] (max rel. error 1.0e-4, below the 16-bit
 // rounding of P), n added straight into the exponent field.  At head_dim 64 the 16/clk/SM MUFU is the binding unit
-// of attention in theory; measured, the softmax warps are issue-slot-bound, so this path is OFF by
-// default (M3R_ATTN_POLY=1 enables it: 3 of every 8 pairs).
+// of attention: POLY of every 8 exponential pairs take this path (shipped default 1, M3R_ATTN_POLY=0..3;
+// more than 1 of 8 is slower - the softmax warps run out of issue slots, profiles/r01_attention_variants.txt).
 struct PolyC { uint64_t magic, c3, c2, c1, c0; };
 __device__ __forceinline__ PolyC make_polyc() {
   PolyC c;
@@ -610,7 +610,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     if (mk3(&tmV1, a->V1, a->ldk1, a->Nk1, a->kv_bstride1, Bkv)) return 1;
   } else { tmK1 = tmK0; tmV1 = tmV0; }
 
-  // ---- shape heuristics (tools/prof_attn.py sweep, profiles/r01_attention_sweep.txt):
+  // ---- shape heuristics (tools/prof_attn.py `sweep` / `longmem`, profiles/r01_attention_variants.txt, profiles/r02_run1_baselines_refgpu_parity.log):
   //  * enough work for ~half a wave of 2-tile CTAs -> QT=2 (K/V tiles shared by two query tiles, ping-pong), no split;
   //  * otherwise (one view per step) QT=1, two CTAs per SM, and the key range split so that ~2 CTAs per SM exist,
   //    keeping at least 4 key tiles per split; the last CTA of a (batch, head, tile) to finish merges the partials.
@@ -619,11 +619,18 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   const int ctas2 = ((a->Nq + 255) / 256) * a->H * a->B;
   const int ctas1 = ((a->Nq + 127) / 128) * a->H * a->B;
   int qt = (a->Nq > 128 && 2 * ctas2 >= sms) ? 2 : 1;
+  //  * one view against a LONG memory (>= ~64 views): two query tiles per CTA halve the K/V bytes each SM pulls per flop,
+  //    which is what bounds the QT=1 form there; the key range is split to fill the SMs (profiles/r02_run1_*: M=100 views
+  //    257 -> 239 us, M=200 497 -> 452 us; below ~50 views QT=1 with splits stays ahead)
+  const bool long_keys = qt == 1 && a->Nq > 128 && key_tiles >= 384 && ctas2 < sms;
+  if (long_keys) qt = 2;
   if (const char* f = getenv("M3R_ATTN_QT")) { const int v = atoi(f); if (v == 1 || v == 2) qt = v; }
   int splits = 1;
   if (qt == 1 && ctas1 < 2 * sms) {
     splits = (2 * sms + ctas1 / 2) / ctas1;
     if (splits > key_tiles / 4) splits = key_tiles / 4;        // a split pays ~2 us of partial store + merge: >= 4 tiles each
+  } else if (qt == 2 && long_keys) {
+    splits = (sms + ctas2 / 2) / ctas2;
   }
   if (const char* f = getenv("M3R_ATTN_SPLITS")) { const int v = atoi(f); if (v >= 1) splits = v; }
   if (splits > key_tiles) splits = key_tiles;

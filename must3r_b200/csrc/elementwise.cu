@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
                                                         const float* __restrict__ add, long long ldadd,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int M, int D, void* __restrict__ out, long long ldo,
-                                                        int out_dtype, int is_bf16) {
+                                                        int out_dtype, int is_bf16, int add_rows, int add_period) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int nv = D >> 2;  // float4 per row
@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
   float4 gv[PRE ? MAXV : 1], bv[PRE ? MAXV : 1];
-  if (PRE) {
+  const bool affine = gamma != nullptr;          // nullptr: plain normalisation (the consumer GEMM's weights carry the affine)
+  if (PRE && affine) {
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int idx = lane + i * 32;
@@ -40,7 +41,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   if (row >= M) return;
   const float4* xr = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xv) + (IN16 ? 0 : (long long)row * ldx));
   const uint2* xh = reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(xv) + (IN16 ? (long long)row * ldx : 0));
-  const float4* ar = add ? reinterpret_cast<const float4*>(add + (long long)row * ldadd) : nullptr;
+  // `add` covers rows < add_rows and repeats with period add_period (one feedback offset for every decoder level)
+  const float4* ar = (add && row < add_rows) ? reinterpret_cast<const float4*>(add + (long long)(row % add_period) * ldadd) : nullptr;
   float4 v[MAXV];
   float s = 0.f;
 #pragma unroll
@@ -76,12 +78,12 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + i * 32;
     if (idx < nv) {
-      const float4 g = PRE ? gv[PRE ? i : 0] : __ldg(g4 + idx), b = PRE ? bv[PRE ? i : 0] : __ldg(b4 + idx);
       float4 y;
-      y.x = (v[i].x - mean) * rstd * g.x + b.x;
-      y.y = (v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (v[i].z - mean) * rstd * g.z + b.z;
-      y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      y.x = (v[i].x - mean) * rstd; y.y = (v[i].y - mean) * rstd; y.z = (v[i].z - mean) * rstd; y.w = (v[i].w - mean) * rstd;
+      if (affine) {
+        const float4 g = PRE ? gv[PRE ? i : 0] : __ldg(g4 + idx), b = PRE ? bv[PRE ? i : 0] : __ldg(b4 + idx);
+        y.x = y.x * g.x + b.x; y.y = y.y * g.y + b.y; y.z = y.z * g.z + b.z; y.w = y.w * g.w + b.w;
+      }
       if (out_dtype == 0) {
         reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + (long long)row * ldo)[idx] = y;
       } else {
@@ -245,10 +247,10 @@ static int grid_for(long long total, int block) {
 
 using namespace m3r;
 
-extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int64_t ldadd, const float* gamma,
-                             const float* beta, float eps, int32_t M, int32_t D, void* out, int64_t ldo,
-                             int32_t out_dtype, int32_t is_bf16, void* stream) {
-  if (!x || !gamma || !beta || !out) return set_error("layernorm: null pointer");
+static int layernorm_impl(const float* x, int64_t ldx, const float* add, int64_t ldadd, int add_rows, int add_period, const float* gamma,
+                          const float* beta, float eps, int32_t M, int32_t D, void* out, int64_t ldo,
+                          int32_t out_dtype, int32_t is_bf16, void* stream) {
+  if (!x || !out) return set_error("layernorm: null pointer");
   if (M <= 0) return 0;
   if (D % 4 || D > 2048 || ldx % 4 || (add && ldadd % 4) || ldo % 4) return set_error("layernorm: D=%d must be a multiple of 4, <= 2048, 16B-aligned rows", D);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -256,12 +258,25 @@ extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int6
   const int grid = (M + wpb - 1) / wpb;
   ProfScope prof(PROF_LN, 0.0, (double)M * D * (4.0 + (add ? 4.0 : 0.0) + (out_dtype ? 2.0 : 4.0)), s);
   if (D <= 1024 && M <= 4096)
-    launch_pdl(layernorm_kernel<8, false, true>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
+    launch_pdl(layernorm_kernel<8, false, true>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16, add_rows, add_period);
   else if (D <= 1024)
-    launch_pdl(layernorm_kernel<8, false, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
+    launch_pdl(layernorm_kernel<8, false, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16, add_rows, add_period);
   else
-    launch_pdl(layernorm_kernel<16, false, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16);
+    launch_pdl(layernorm_kernel<16, false, false>, dim3(grid), dim3(wpb * 32), 0, s, (const void*)x, (long long)ldx, add, (long long)ldadd, gamma, beta, eps, (int)M, (int)D, out, (long long)ldo, (int)out_dtype, (int)is_bf16, add_rows, add_period);
   return check_launch("layernorm");
+}
+
+extern "C" int m3r_layernorm(const float* x, int64_t ldx, const float* add, int64_t ldadd, const float* gamma,
+                             const float* beta, float eps, int32_t M, int32_t D, void* out, int64_t ldo,
+                             int32_t out_dtype, int32_t is_bf16, void* stream) {
+  if (!gamma || !beta) return set_error("layernorm: null pointer");
+  return layernorm_impl(x, ldx, add, ldadd, M, 1 << 30, gamma, beta, eps, M, D, out, ldo, out_dtype, is_bf16, stream);
+}
+
+extern "C" int m3r_normalize16(const float* x, int64_t ldx, const float* add, int64_t ldadd, int32_t add_rows, int32_t add_period,
+                               float eps, int32_t M, int32_t D, void* out16, int64_t ldo, int32_t is_bf16, void* stream) {
+  if (add && (add_rows < 0 || add_period <= 0)) return set_error("normalize16: bad add_rows / add_period");
+  return layernorm_impl(x, ldx, add, ldadd, add ? add_rows : 0, add ? add_period : 1, nullptr, nullptr, eps, M, D, out16, ldo, M3R_OUT_16, is_bf16, stream);
 }
 
 extern "C" int m3r_layernorm16(const void* x16, int64_t ldx, const float* gamma, const float* beta, float eps, int32_t M,
@@ -275,9 +290,9 @@ extern "C" int m3r_layernorm16(const void* x16, int64_t ldx, const float* gamma,
   ProfScope prof(PROF_LN, 0.0, (double)M * D * 4.0, s);
   const float* none = nullptr;
   if (D <= 1024)
-    launch_pdl(layernorm_kernel<8, true, false>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16);
+    launch_pdl(layernorm_kernel<8, true, false>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16, 0, 1);
   else
-    launch_pdl(layernorm_kernel<16, true, false>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16);
+    launch_pdl(layernorm_kernel<16, true, false>, dim3(grid), dim3(wpb * 32), 0, s, x16, (long long)ldx, none, 0LL, gamma, beta, eps, (int)M, (int)D, out16, (long long)ldo, 1, (int)is_bf16, 0, 1);
   return check_launch("layernorm16");
 }
 

@@ -20,8 +20,10 @@ constexpr int SMEM_BUDGET = 196608;  // bytes of operand ring
 template <int BN>
 struct GemmCfg {
   static constexpr int STAGE_BYTES = (BM + BN) * BK * 2;
-  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;   // 256:4  128:6  64:8
-  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;   // 256:4  192:4  160:5  128:6  64:8
+  static constexpr int TMEM_COLS = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;   // power of two
+  static constexpr int NCHUNK = BN / 32;                     // 32-column epilogue chunks
+  static constexpr int CH0 = (NCHUNK + 1) / 2;               // chunks drained by the first warp of a lane quarter; the second takes the rest
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -45,20 +47,37 @@ struct GemmParams {
   void* peer_out[M3R_MAX_PEERS];
   unsigned long long* trace;   // debug only (m3r_debug_trace): 16 words per CTA; normally null
   int w_static;                // weights may be requested before the programmatic-dependency wait
+  // ---- grouped GEMM: `groups` independent problems of M rows each that share the shapes: A rows [g*M, (g+1)*M) of one
+  // [groups*M, K] matrix, W rows [g*w_group_rows, +N), bias + g*bias_group, outputs from GemmGroupTab (groups == 1: `out`)
+  int groups;
+  long long w_group_rows, bias_group;
+  // ---- LayerNorm emitted by the epilogue (EMIT kernels): besides `out` (fp32 x = acc + bias + residual) the CTAs of one
+  // m-tile exchange per-row (mean, M2) partials through `stats`, meet at a device-scope counter and write the normalised
+  // row (x - mean) * rstd as 16-bit into norm_out - the A operand of the next GEMM, whose weights carry the affine.
+  void* norm_out;
+  long long ldn;
+  float norm_eps;
+  float2* stats;               // [tiles_m][2 * tiles_n][128]
+  unsigned int* sync;          // [tiles_m][2]: arrivals, departures (both zero between launches)
+};
+
+// output pointers of a grouped GEMM (passed by value: kernel parameter space)
+struct GemmGroupTab {
+  void* out[M3R_MAX_GROUPS];
+  void* peer[M3R_MAX_GROUPS][M3R_MAX_PEERS];
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
-// Epilogue of one 32-column chunk of one accumulator row: bias, RoPE, row bias, GELU, residual, store.
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&raw)[32], int row, bool row_ok, long long orow,
-                                               bool rb_on, const float* rope_row, int col0) {
-  float v[32];
+// Epilogue arithmetic of one 32-column chunk of one accumulator row: bias, RoPE, row bias, GELU, residual -> v[32].
+__device__ __forceinline__ void epilogue_math(const GemmParams& p, const float* bias, const uint32_t (&raw)[32], float (&v)[32], int row,
+                                              bool row_ok, bool rb_on, const float* rope_row, int col0) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
-  if (p.bias) {
+  if (bias) {
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col0 + i));
       v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
     }
   }
@@ -90,40 +109,71 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
   }
-  if (row_ok) {
-    if (p.residual) {
-      const float4* r4 = reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col0);
+  if (row_ok && p.residual) {
+    const float4* r4 = reinterpret_cast<const float4*>(p.residual + (long long)row * p.ldr + col0);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 r = r4[i];
-        v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
-      }
-    }
-    if (p.out_dtype == 0) {
-      float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldc + col0);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
-      uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + orow * p.ldc + col0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 w;
-        w.x = pack16(v[8 * i], v[8 * i + 1], p.is_bf16);
-        w.y = pack16(v[8 * i + 2], v[8 * i + 3], p.is_bf16);
-        w.z = pack16(v[8 * i + 4], v[8 * i + 5], p.is_bf16);
-        w.w = pack16(v[8 * i + 6], v[8 * i + 7], p.is_bf16);
-        o4[i] = w;
-        // fused all-gather: the same 16 bytes go to the other GPUs' copies of the buffer (NVLink peer stores)
-        for (int pr = 0; pr < p.n_peer_out; ++pr)
-          reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.peer_out[pr]) + orow * p.ldc + col0)[i] = w;
-      }
+    for (int i = 0; i < 8; ++i) {
+      const float4 r = r4[i];
+      v[4 * i] += r.x; v[4 * i + 1] += r.y; v[4 * i + 2] += r.z; v[4 * i + 3] += r.w;
     }
   }
 }
 
-template <int BN>
+// Store of one chunk: fp32 or 16-bit row segment; the 16-bit form optionally also goes to the peers' buffers.
+// A peer store instruction of a warp covers 32 rows x 16 B; the four uint4 of a thread complete a 64-byte segment per
+// row back to back, so NVLink sees 64 B write bursts (the fused GEMM -> all-gather path).
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, void* out, void* const* peers, const float (&v)[32], long long orow, int col0) {
+  if (p.out_dtype == 0) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + orow * p.ldc + col0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    uint4 w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      w[i].x = pack16(v[8 * i], v[8 * i + 1], p.is_bf16);
+      w[i].y = pack16(v[8 * i + 2], v[8 * i + 3], p.is_bf16);
+      w[i].z = pack16(v[8 * i + 4], v[8 * i + 5], p.is_bf16);
+      w[i].w = pack16(v[8 * i + 6], v[8 * i + 7], p.is_bf16);
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + orow * p.ldc + col0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o4[i] = w[i];
+    for (int pr = 0; pr < p.n_peer_out; ++pr) {
+      uint4* q4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(peers[pr]) + orow * p.ldc + col0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) q4[i] = w[i];
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&raw)[32], int row, bool row_ok, long long orow,
+                                               bool rb_on, const float* rope_row, int col0) {
+  float v[32];
+  epilogue_math(p, p.bias, raw, v, row, row_ok, rb_on, rope_row, col0);
+  if (row_ok) epilogue_store(p, p.out, p.peer_out, v, orow, col0);
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int atom_add_release_u32(unsigned int* p, unsigned int v) {
+  unsigned int o;
+  asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;" : "=r"(o) : "l"(p), "r"(v) : "memory");
+  return o;
+}
+
+constexpr int MODE_PLAIN = 0, MODE_EMIT = 1, MODE_GROUPED = 2;
+struct NoTab {};
+template <int MODE> struct TabOf { using type = NoTab; };
+template <> struct TabOf<MODE_GROUPED> { using type = GemmGroupTab; };
+
+template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmParams p,
+            const __grid_constant__ typename TabOf<MODE>::type tab) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -140,10 +190,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   M3R_TR(unsigned long long* tr = p.trace ? p.trace + 16ull * blockIdx.x : nullptr;
          if (tr && threadIdx.x == 0) { tr[0] = gtime_ns(); tr[8] = smid(); })
   const int warp = threadIdx.x >> 5;
-  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_mg = (p.M + BM - 1) / BM;          // m-tiles per group
+  const int tiles_m = tiles_mg * p.groups;
   const int tiles_n = p.N / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / BK;
+  // tile t -> (group g, m-tile inside the group, n-tile); m-fastest so that co-resident CTAs share the weight tile in L2
+  auto a_row0 = [&](int tm) { return (tm / tiles_mg) * p.M + (tm % tiles_mg) * BM; };      // first A row of m-tile tm
+  auto w_row0 = [&](int tm, int tn) { return (long long)(tm / tiles_mg) * p.w_group_rows + (long long)tn * BN; };
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
@@ -170,7 +224,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // activations follow after the wait; each stage's barrier expects both halves.
       int pre = 0;
       if (p.w_static && blockIdx.x < num_tiles) {
-        const int n0 = (blockIdx.x / tiles_m) * BN;
+        const int n0 = (int)w_row0(blockIdx.x % tiles_m, blockIdx.x / tiles_m);
         pre = num_kb < STAGES ? num_kb : STAGES;
         for (int kb = 0; kb < pre; ++kb) {
           mbar_arrive_expect_tx(&full[kb], Cfg::STAGE_BYTES);
@@ -182,8 +236,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       M3R_TR(if (tr) tr[2] = gtime_ns();)
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % tiles_m) * BM;
-        const int n0 = (t / tiles_m) * BN;
+        const int m0 = a_row0(t % tiles_m);
+        const int n0 = (int)w_row0(t % tiles_m, t / tiles_m);
         for (int kb = 0; kb < num_kb; ++kb) {
           if (pre > 0) {                      // stage already armed, W half in flight
             --pre;
@@ -239,33 +293,112 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     griddep_wait();
     griddep_launch();
     const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
-    const int chalf = (warp - 2) >> 2;            // which half of the tile's columns this warp drains
+    const int chalf = (warp - 2) >> 2;            // which share of the tile's 32-column chunks this warp drains
+    const int c_lo = chalf == 0 ? 0 : Cfg::CH0, c_hi = chalf == 0 ? Cfg::CH0 : Cfg::NCHUNK;
     const int lane = threadIdx.x & 31;
     int as = 0; uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % tiles_m) * BM;
-      const int n0 = (t / tiles_m) * BN;
-      const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      long long orow = row;
-      if (p.rows_per_batch > 0) orow = (long long)(row / p.rows_per_batch) * p.batch_stride_rows + row % p.rows_per_batch;
-      const bool rb_on = p.rowbias != nullptr && (row % p.rb_period) >= p.rb_first;
-      const float* rope_row = p.rope_tab ? p.rope_tab + (long long)(row % p.rope_period) * 64 : nullptr;
+      const int tm = t % tiles_m, tn = t / tiles_m;
+      const int g = tm / tiles_mg;
+      const int lrow = (tm % tiles_mg) * BM + quarter * 32 + lane;      // row inside the group
+      const int n0 = tn * BN;
+      const bool row_ok = lrow < p.M;
+      long long orow = lrow;
+      if (p.rows_per_batch > 0) orow = (long long)(lrow / p.rows_per_batch) * p.batch_stride_rows + lrow % p.rows_per_batch;
+      const bool rb_on = p.rowbias != nullptr && (lrow % p.rb_period) >= p.rb_first;
+      const float* rope_row = p.rope_tab ? p.rope_tab + (long long)(lrow % p.rope_period) * 64 : nullptr;
+      const float* bias = p.bias ? p.bias + (long long)g * p.bias_group : nullptr;
 
       mbar_wait(&tfull[as], aphase);
       M3R_TR(if (tr && threadIdx.x == 64) tr[6] = gtime_ns();)
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(quarter * 32) << 16) + as * BN;
-#pragma unroll 1
-      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+      if (MODE == MODE_EMIT) {
+        // ---- x = acc + bias + residual -> out (fp32); the thread keeps its BN/2 values for the normalisation
+        static_assert(MODE != MODE_EMIT || BN == 64, "LayerNorm-emitting epilogue: one 32-column chunk per thread");
         uint32_t raw[32];
-        tmem_ld32(t_addr + c * 32, raw);
+        tmem_ld32(t_addr + c_lo * 32, raw);
         tmem_wait_ld();
-        if (c == (chalf + 1) * (BN / 64) - 1) {  // this warp's share of the accumulator is read: hand it back early
+        tc_fence_before();
+        mbar_arrive(&tempty[as]);
+        float v[32];
+        epilogue_math(p, bias, raw, v, lrow, row_ok, rb_on, rope_row, n0 + c_lo * 32);
+        if (!row_ok) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+        } else {
+          epilogue_store(p, p.out, p.peer_out, v, orow, n0 + c_lo * 32);
+        }
+        // two-pass statistics of the thread's 32 values, combined across the row's 2 * tiles_n partials with Chan's
+        // formula (as accurate as a two-pass LayerNorm over the whole row)
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) { s0 += v[i]; s1 += v[i + 1]; }
+        const float mu = (s0 + s1) * (1.0f / 32.0f);
+        float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) { const float a = v[i] - mu, b = v[i + 1] - mu; q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1); }
+        const int parts = 2 * tiles_n;
+        const int rit = quarter * 32 + lane;                       // row in tile
+        float2* st = p.stats + ((long long)tm * parts) * BM;
+        st[(long long)(tn * 2 + chalf) * BM + rit] = make_float2(mu, q0 + q1);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        unsigned int* cnt = p.sync + 2 * tm;
+        if (warp == 2 && lane == 0) {
+          atom_add_release_u32(cnt, 1u);
+          unsigned int spins = 0;
+          while (ld_acquire_u32(cnt) < (unsigned int)tiles_n) { if (++spins > (1u << 26)) __trap(); }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float msum = 0.f;
+        float2 pr[24];
+        const int np = parts <= 24 ? parts : 24;                   // host guarantees parts <= 24
+#pragma unroll
+        for (int i = 0; i < 24; ++i) if (i < np) { pr[i] = __ldcg(st + (long long)i * BM + rit); msum += pr[i].x; }
+        const float mean = msum / (float)np;
+        float m2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) if (i < np) { const float d = pr[i].x - mean; m2 += pr[i].y + 32.0f * d * d; }
+        const float rstd = rsqrtf(m2 / (32.0f * (float)np) + p.norm_eps);
+        if (row_ok) {
+          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.norm_out) + (long long)lrow * p.ldn + n0 + c_lo * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 w;
+            w.x = pack16((v[8 * i] - mean) * rstd, (v[8 * i + 1] - mean) * rstd, p.is_bf16);
+            w.y = pack16((v[8 * i + 2] - mean) * rstd, (v[8 * i + 3] - mean) * rstd, p.is_bf16);
+            w.z = pack16((v[8 * i + 4] - mean) * rstd, (v[8 * i + 5] - mean) * rstd, p.is_bf16);
+            w.w = pack16((v[8 * i + 6] - mean) * rstd, (v[8 * i + 7] - mean) * rstd, p.is_bf16);
+            o4[i] = w;
+          }
+        }
+        // departure: the last CTA of the m-tile to have read the partials re-arms both counters for the next launch
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (warp == 2 && lane == 0) {
+          if (atomicAdd(cnt + 1, 1u) == (unsigned int)tiles_n - 1u) { cnt[1] = 0u; __threadfence(); cnt[0] = 0u; }
+        }
+      } else {
+        void* out_g = p.out;
+        void* const* peers_g = p.peer_out;
+        if constexpr (MODE == MODE_GROUPED) { out_g = tab.out[g]; peers_g = tab.peer[g]; }
+        if (c_lo == c_hi) {                       // narrow tiles: this warp has no chunk, it only returns the buffer
           tc_fence_before();
           mbar_arrive(&tempty[as]);
         }
-        epilogue_chunk(p, raw, row, row_ok, orow, rb_on, rope_row, n0 + c * 32);
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; ++c) {
+          uint32_t raw[32];
+          tmem_ld32(t_addr + c * 32, raw);
+          tmem_wait_ld();
+          if (c == c_hi - 1) {  // this warp's share of the accumulator is read: hand it back early
+            tc_fence_before();
+            mbar_arrive(&tempty[as]);
+          }
+          float v[32];
+          epilogue_math(p, bias, raw, v, lrow, row_ok, rb_on, rope_row, n0 + c * 32);
+          if (row_ok) epilogue_store(p, out_g, peers_g, v, orow, n0 + c * 32);
+        }
       }
       M3R_TR(if (tr && threadIdx.x == 64) tr[7] = gtime_ns();)
       if (++as == 2) { as = 0; aphase ^= 1; }
@@ -281,13 +414,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
-template <int BN>
-static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  CUtensorMap tmA, tmW;
-  if (make_tmap_2d(&tmA, a->A, a->is_bf16, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM)) return 1;
-  if (make_tmap_2d(&tmW, a->W, a->is_bf16, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, BK, BN)) return 1;
-  GemmParams p;
+static void fill_params(GemmParams& p, const m3r_gemm_args* a) {
   p.M = a->M; p.N = a->N; p.K = a->K; p.is_bf16 = a->is_bf16;
   p.bias = a->bias; p.act = a->act; p.residual = a->residual; p.ldr = a->ldr;
   p.rowbias = a->rowbias; p.rb_period = a->rb_period > 0 ? a->rb_period : 1; p.rb_first = a->rb_first;
@@ -298,17 +425,66 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream) {
   p.trace = trace_buffer();
   p.w_static = a->w_static;
   for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-    if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+  p.groups = 1; p.w_group_rows = 0; p.bias_group = 0;
+  p.norm_out = nullptr; p.ldn = 0; p.norm_eps = 0.f; p.stats = nullptr; p.sync = nullptr;
+}
+
+// Scratch of the LayerNorm-emitting epilogue, one per device: partial row statistics + arrival / departure counters.
+// Only kernels of ONE stream at a time may use it (they spin on each other's CTAs): the model code emits on the
+// caller's stream only, never on its side streams.
+struct EmitScratch { float2* stats = nullptr; unsigned int* sync = nullptr; };
+constexpr int EMIT_MAX_TILES_M = 16, EMIT_MAX_PARTS = 24;
+static EmitScratch* emit_scratch() {
+  static EmitScratch per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  EmitScratch& e = per_dev[dev];
+  if (!e.stats) {
+    void* a = nullptr; void* b = nullptr;
+    if (cudaMalloc(&a, sizeof(float2) * EMIT_MAX_TILES_M * EMIT_MAX_PARTS * BM) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&b, sizeof(unsigned int) * 2 * EMIT_MAX_TILES_M) != cudaSuccess) { cudaFree(a); return nullptr; }
+    if (cudaMemset(b, 0, sizeof(unsigned int) * 2 * EMIT_MAX_TILES_M) != cudaSuccess) { cudaFree(a); cudaFree(b); return nullptr; }
+    e.stats = reinterpret_cast<float2*>(a); e.sync = reinterpret_cast<unsigned int*>(b);
   }
-  const int tiles = ((a->M + BM - 1) / BM) * (a->N / BN);
+  return &e;
+}
+
+template <int BN, int MODE>
+static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream, const m3r_gemm_group* grp = nullptr) {
+  using Cfg = GemmCfg<BN>;
+  const int groups = (MODE == MODE_GROUPED) ? grp->groups : 1;
+  CUtensorMap tmA, tmW;
+  if (make_tmap_2d(&tmA, a->A, a->is_bf16, (uint64_t)a->K, (uint64_t)a->M * groups, (uint64_t)a->lda, BK, BM)) return 1;
+  if (make_tmap_2d(&tmW, a->W, a->is_bf16, (uint64_t)a->K, MODE == MODE_GROUPED ? (uint64_t)((groups - 1) * grp->w_group_rows + a->N) : (uint64_t)a->N, (uint64_t)a->ldw, BK, BN)) return 1;
+  GemmParams p;
+  fill_params(p, a);
+  typename TabOf<MODE>::type tab;
+  const int tiles = ((a->M + BM - 1) / BM) * groups * (a->N / BN);
+  if constexpr (MODE == MODE_GROUPED) {
+    p.groups = groups; p.w_group_rows = grp->w_group_rows; p.bias_group = grp->bias_group;
+    for (int g = 0; g < M3R_MAX_GROUPS; ++g) {
+      tab.out[g] = g < groups ? grp->out[g] : nullptr;
+      for (int r = 0; r < M3R_MAX_PEERS; ++r) tab.peer[g][r] = (g < groups && r < a->n_peer_out) ? grp->peer_out[g * M3R_MAX_PEERS + r] : nullptr;
+    }
+  }
+  if constexpr (MODE == MODE_EMIT) {
+    EmitScratch* e = emit_scratch();
+    if (!e) return set_error("gemm: LayerNorm-emit scratch allocation failed");
+    p.norm_out = a->norm_out; p.ldn = a->ldn; p.norm_eps = a->norm_eps; p.stats = e->stats; p.sync = e->sync;
+  }
+  static bool attr_set[64] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set[dev] = true;
+  }
   const int grid = tiles < num_sms() ? tiles : num_sms();
+  if (MODE == MODE_EMIT && tiles > grid) return set_error("gemm: LayerNorm-emitting epilogue needs one tile per CTA (%d tiles, %d SMs)", tiles, grid);
   {
-    ProfScope prof(BN == 256 ? PROF_GEMM256 : (BN == 128 ? PROF_GEMM128 : PROF_GEMM64), 2.0 * a->M * (double)a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + (double)a->M * a->N * (a->out_dtype ? 2 : 4), stream);
-    cudaError_t le = launch_pdl(gemm_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmW, p);
+    const int cat = BN >= 256 ? PROF_GEMM256 : (BN >= 128 ? PROF_GEMM128 : PROF_GEMM64);
+    ProfScope prof(cat, 2.0 * a->M * groups * (double)a->N * a->K, 2.0 * ((double)a->M * groups * a->K + (double)a->N * groups * a->K) + (double)a->M * groups * a->N * (a->out_dtype ? 2 : 4), stream);
+    cudaError_t le = launch_pdl(gemm_kernel<BN, MODE>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmW, p, tab);
     if (le != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(le));
   }
   cudaError_t e = cudaGetLastError();
@@ -459,21 +635,13 @@ static int launch_gemm_pair(const m3r_gemm_args* a, cudaStream_t stream) {
   if (make_tmap_2d(&tmA, a->A, a->is_bf16, (uint64_t)a->K, (uint64_t)a->M, (uint64_t)a->lda, BK, 128)) return 1;
   if (make_tmap_2d(&tmW, a->W, a->is_bf16, (uint64_t)a->K, (uint64_t)a->N, (uint64_t)a->ldw, BK, 128)) return 1;
   GemmParams p;
-  p.M = a->M; p.N = a->N; p.K = a->K; p.is_bf16 = a->is_bf16;
-  p.bias = a->bias; p.act = a->act; p.residual = a->residual; p.ldr = a->ldr;
-  p.rowbias = a->rowbias; p.rb_period = a->rb_period > 0 ? a->rb_period : 1; p.rb_first = a->rb_first;
-  p.rope_tab = a->rope_tab; p.rope_cols = a->rope_cols; p.rope_period = a->rope_period > 0 ? a->rope_period : 1;
-  p.out = a->out; p.ldc = a->ldc; p.out_dtype = a->out_dtype;
-  p.rows_per_batch = a->rows_per_batch; p.batch_stride_rows = a->batch_stride_rows;
-  p.n_peer_out = a->n_peer_out;
-  p.trace = trace_buffer();
-  p.w_static = a->w_static;
-  for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
+  fill_params(p, a);
+  static bool attr_set[64] = {};
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
     if (e != cudaSuccess) return set_error("gemm(pair): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   const int tiles = ((a->M + 255) / 256) * (a->N / 256);
   int pairs = num_sms() / 2;
@@ -489,26 +657,51 @@ static int launch_gemm_pair(const m3r_gemm_args* a, cudaStream_t stream) {
   return 0;
 }
 
-}  // namespace m3r
-
-extern "C" int m3r_gemm(const m3r_gemm_args* a, void* stream) {
-  using namespace m3r;
-  if (!a || !a->A || !a->W || !a->out) return set_error("gemm: null pointer");
-  if (a->M <= 0) return 0;
-  if (a->N % 64 || a->K % 64 || a->N <= 0 || a->K <= 0) return set_error("gemm: N (%d) and K (%d) must be multiples of 64", a->N, a->K);
+static int check_args(const m3r_gemm_args* a) {
+  if (!a || !a->A || !a->W) return set_error("gemm: null pointer");
+  if (a->N % 32 || a->K % 64 || a->N <= 0 || a->K <= 0) return set_error("gemm: N (%d) must be a multiple of 32 and K (%d) of 64", a->N, a->K);
   if (a->lda % 8 || a->ldw % 8) return set_error("gemm: lda/ldw must be multiples of 8 elements (16 B)");
   if ((a->out_dtype == M3R_OUT_F32 && a->ldc % 4) || (a->out_dtype == M3R_OUT_16 && a->ldc % 8)) return set_error("gemm: ldc alignment");
   if (a->residual && a->ldr % 4) return set_error("gemm: ldr alignment");
   if (a->rope_tab && (a->rope_cols % 64)) return set_error("gemm: rope_cols must be a multiple of 64");
   if (a->n_peer_out < 0 || a->n_peer_out > M3R_MAX_PEERS || (a->n_peer_out > 0 && a->out_dtype != M3R_OUT_16)) return set_error("gemm: peer outputs need 0..%d pointers and a 16-bit output", M3R_MAX_PEERS);
-  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // Tile-width heuristic: widest BN that still yields about one wave of CTAs.
-  const int tiles_m = (a->M + BM - 1) / BM;
+  return 0;
+}
+
+// Tile width for the 1-CTA kernel.  One-wave problems (the one-view chain) are bound by the per-SM L2->smem ingest, i.e. by
+// the bytes ONE CTA has to pull: K * (128 + BN) * 2 - so the narrowest tile that still fits in one wave wins (most SMs
+// busy, least bytes per SM).  Multi-wave problems take the widest tile that keeps every SM busy (fewer re-reads of A).
+static int pick_bn(int M, int N, int groups) {
+  const int tiles_m = ((M + BM - 1) / BM) * groups;
   const int sms = num_sms();
-  // (profiles/r01_small_gemm_tiles.txt: at M=768, BN=128 wins from ~100 tiles up, BN=64 below)
-  int bn = 64;
-  if (a->N % 256 == 0 && tiles_m * (a->N / 256) >= sms) bn = 256;
-  else if (a->N % 128 == 0 && tiles_m * (a->N / 128) >= (sms * 2) / 3) bn = 128;
+  static const int cand[] = {64, 128, 160, 192, 256};
+  for (int bn : cand)
+    if (N % bn == 0 && tiles_m * (N / bn) <= sms) return bn;
+  if (N % 256 == 0 && tiles_m * (N / 256) >= sms) return 256;
+  if (N % 128 == 0 && tiles_m * (N / 128) >= (sms * 2) / 3) return 128;
+  if (N % 64 == 0) return 64;
+  if (N % 160 == 0) return 160;
+  return 32;
+}
+
+}  // namespace m3r
+
+extern "C" int m3r_gemm(const m3r_gemm_args* a, void* stream) {
+  using namespace m3r;
+  if (check_args(a)) return 1;
+  if (!a->out) return set_error("gemm: null pointer");
+  if (a->M <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int sms = num_sms();
+  if (a->norm_out) {
+    // LayerNorm-emitting epilogue: fp32 out = the new residual stream, norm_out = its normalised 16-bit rows
+    if (a->N % 64 || a->N > 32 * EMIT_MAX_PARTS || a->out_dtype != M3R_OUT_F32 || a->ldn % 8)
+      return set_error("gemm: norm_out needs N %% 64 == 0, N <= %d, an fp32 output and ldn %% 8 == 0", 32 * EMIT_MAX_PARTS);
+    const int tiles_m = (a->M + BM - 1) / BM;
+    if (tiles_m > EMIT_MAX_TILES_M || tiles_m * (a->N / 64) > sms)
+      return set_error("gemm: norm_out needs one 128x64 tile per SM (M=%d N=%d); normalise with m3r_layernorm instead", a->M, a->N);
+    return launch_gemm<64, MODE_EMIT>(a, s);
+  }
   {
     // CTA-pair kernel for problems with at least one 256x256 tile per SM pair.  Measured (profiles/r01_run13_gemm_pair.log):
     // +7..+20 % for K >= 1024, -1..-4 % for K = 768 (epilogue-bound tiles) -> used for K >= 1024; M3R_GEMM_PAIR=0/2
@@ -518,11 +711,36 @@ extern "C" int m3r_gemm(const m3r_gemm_args* a, void* stream) {
     const bool eligible = a->N % 256 == 0 && ((a->M + 255) / 256) * (a->N / 256) >= sms / 2 && !getenv("M3R_GEMM_BN");
     if (eligible && (pair_mode == 2 || (pair_mode == 1 && a->K >= 1024))) return launch_gemm_pair(a, s);
   }
+  int bn = pick_bn(a->M, a->N, 1);
   const char* force = getenv("M3R_GEMM_BN");
-  if (force) { int f = atoi(force); if ((f == 64 || f == 128 || f == 256) && a->N % f == 0) bn = f; }
+  if (force) { int f = atoi(force); if ((f == 32 || f == 64 || f == 128 || f == 160 || f == 192 || f == 256) && a->N % f == 0) bn = f; }
   switch (bn) {
-    case 256: return launch_gemm<256>(a, s);
-    case 128: return launch_gemm<128>(a, s);
-    default: return launch_gemm<64>(a, s);
+    case 256: return launch_gemm<256, MODE_PLAIN>(a, s);
+    case 192: return launch_gemm<192, MODE_PLAIN>(a, s);
+    case 160: return launch_gemm<160, MODE_PLAIN>(a, s);
+    case 128: return launch_gemm<128, MODE_PLAIN>(a, s);
+    case 64: return launch_gemm<64, MODE_PLAIN>(a, s);
+    default: return launch_gemm<32, MODE_PLAIN>(a, s);
+  }
+}
+
+// `groups` GEMMs of identical shape in one launch (the post-feedback K|V projections of all decoder levels,
+// must3r/model/decoder.py:323-330): A = [groups * M, K] (group g = rows [g*M, (g+1)*M)), W / bias stacked with strides
+// w_group_rows / bias_group, one output (and one set of peer outputs) per group.
+extern "C" int m3r_gemm_grouped(const m3r_gemm_args* a, const m3r_gemm_group* grp, void* stream) {
+  using namespace m3r;
+  if (check_args(a)) return 1;
+  if (!grp || grp->groups < 1 || grp->groups > M3R_MAX_GROUPS) return set_error("gemm_grouped: 1..%d groups", M3R_MAX_GROUPS);
+  if (a->norm_out || a->residual) return set_error("gemm_grouped: no residual / norm_out");
+  for (int g = 0; g < grp->groups; ++g) if (!grp->out[g]) return set_error("gemm_grouped: out[%d] is null", g);
+  if (a->M <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int bn = pick_bn(a->M, a->N, grp->groups);
+  if (bn != 256 && bn != 128) bn = a->N % 128 == 0 ? 128 : 64;
+  if (a->N % bn) return set_error("gemm_grouped: N (%d) must be a multiple of 64", a->N);
+  switch (bn) {
+    case 256: return launch_gemm<256, MODE_GROUPED>(a, s, grp);
+    case 128: return launch_gemm<128, MODE_GROUPED>(a, s, grp);
+    default: return launch_gemm<64, MODE_GROUPED>(a, s, grp);
   }
 }

@@ -33,7 +33,7 @@ static int gemm(const void* A, int64_t lda, const void* W, int64_t ldw, int M, i
                 void* stream, const float* rope_tab = nullptr, int rope_cols = 0, int rope_period = 0,
                 const float* rowbias = nullptr, int rb_period = 1, int rb_first = 0, int rows_per_batch = 0,
                 int64_t batch_stride_rows = 0, int n_peer_out = 0, void* const* peer_out = nullptr) {
-  m3r_gemm_args a;
+  m3r_gemm_args a = {};
   a.n_peer_out = n_peer_out;
   a.w_static = 1;                  // every GEMM of the model multiplies by checkpoint weights
   for (int i = 0; i < M3R_MAX_PEERS; ++i) a.peer_out[i] = i < n_peer_out ? peer_out[i] : nullptr;
@@ -110,9 +110,9 @@ extern "C" int m3r_encoder_forward(const m3r_encoder_weights* w, const float* im
 // ------------------------------------------------------------------------------------------------ decoder
 namespace m3r {
 
-// Side stream for work that is independent of the main chain inside an update step (the K|V projection of the new
-// tokens, half of the post-feedback K|V rows): one-view steps launch kernels of <= 72..144 CTAs, so two of them fit
-// on the 148 SMs at once.  Fork / join with events; M3R_SIDE_STREAM=0 disables it.
+// Side streams, one set per device: `s` runs the feedback MLP and the memory append (post-feedback K|V of every level)
+// concurrently with the last decoder block and the head; `copy` moves the old memory rows when the caller wants a fresh
+// concatenated tensor.  Fork / join with events; M3R_SIDE_STREAM=0 disables them.
 struct SideStream {
   cudaStream_t s = nullptr, copy = nullptr;
   cudaEvent_t ev[32];
@@ -124,24 +124,33 @@ struct SideStream {
     if (e && e[0] == '0') { enabled = false; return; }
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { enabled = false; return; }
     if (cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking) != cudaSuccess) { enabled = false; return; }
-    for (int i = 0; i < 32; ++i) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    for (int i = 0; i < 32; ++i)
+      if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) { enabled = false; return; }
     ok = true;
   }
   // make `to` wait for everything enqueued on `from` so far
-  void link(cudaStream_t from, cudaStream_t to) {
+  int link(cudaStream_t from, cudaStream_t to) {
     cudaEvent_t e = ev[next]; next = (next + 1) & 31;
-    cudaEventRecord(e, from);
-    cudaStreamWaitEvent(to, e, 0);
+    cudaError_t r = cudaEventRecord(e, from);
+    if (r == cudaSuccess) r = cudaStreamWaitEvent(to, e, 0);
+    return r == cudaSuccess ? 0 : set_error("decoder_forward: stream fork/join failed: %s", cudaGetErrorString(r));
   }
 };
-static SideStream g_side;
+static SideStream* side_streams() {
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  return &per_dev[dev];
+}
 
 struct DecWs {
-  uint16_t *enc16, *h16, *h16b, *qkv16, *q16, *att16, *mlp16, *kvnew;
+  uint16_t *enc16, *h16, *big16, *q16, *att16, *mlp16, *kvnew;
+  uint16_t *hfb16, *mlpfb16, *hpost16;   // side stream: feedback MLP operands, normalised (new_mem[l] + offset) of every level
   uint16_t *kvmem, *memln;     // memory_mode norm_y / raw: K|V of the stored memory projected at use; LN_y of raw rows
   float *x, *tmp, *snap, *off, *rope, *headout;
   int64_t M, Nt;
   int nbm;                     // distinct memory batches behind kvmem (1 when the memory is a stride-0 expand)
+  bool merged;                 // one scene, one aspect ratio: K|V of the new tokens live in big16 (no kvnew buffer)
   std::vector<int64_t> row0;   // first row of each group
   std::vector<int64_t> tok0;   // first new-token index (per scene) of each group
 };
@@ -156,25 +165,27 @@ static int64_t dec_layout(const m3r_decoder_weights* w, const m3r_decoder_call* 
     Nt += (int64_t)c->groups[g].n_views * c->groups[g].N;
   }
   ws->M = M; ws->Nt = Nt;
+  ws->merged = !c->render && c->B == 1 && c->G == 1;
   Arena a(base, cap);
   ws->rope = a.take<float>(M * 64);
   ws->enc16 = a.take<uint16_t>(M * w->enc_dim);
   ws->x = a.take<float>(M * D);
   ws->tmp = a.take<float>(M * D);
   ws->h16 = a.take<uint16_t>(M * D);
-  ws->qkv16 = a.take<uint16_t>(M * 3 * D);
+  ws->big16 = a.take<uint16_t>(M * (ws->merged ? 5 : 3) * D);
   ws->q16 = a.take<uint16_t>(M * D);
   ws->att16 = a.take<uint16_t>(M * D);
   const int64_t hid = w->mlp_hidden > 4 * D ? w->mlp_hidden : 4 * D;
   ws->mlp16 = a.take<uint16_t>(M * hid);
   ws->headout = a.take<float>(M * w->out_dim);
+  ws->snap = nullptr; ws->off = nullptr; ws->kvnew = nullptr; ws->hfb16 = ws->mlpfb16 = ws->hpost16 = nullptr;
   if (!c->render) {
     ws->snap = a.take<float>((int64_t)w->depth * M * D);
     ws->off = a.take<float>(M * D);
-    ws->kvnew = a.take<uint16_t>((int64_t)c->B * Nt * 2 * D);
-    ws->h16b = a.take<uint16_t>(M * D);
-  } else {
-    ws->snap = nullptr; ws->off = nullptr; ws->kvnew = nullptr; ws->h16b = nullptr;
+    if (!ws->merged) ws->kvnew = a.take<uint16_t>((int64_t)c->B * Nt * 2 * D);
+    ws->hfb16 = a.take<uint16_t>(M * D);
+    ws->mlpfb16 = a.take<uint16_t>(M * 4 * D);
+    ws->hpost16 = a.take<uint16_t>((int64_t)w->depth * M * D);
   }
   ws->kvmem = ws->memln = nullptr; ws->nbm = 0;
   if (c->mem_mode != M3R_MEM_KV && c->Nm > 0) {
@@ -209,32 +220,64 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   if (need > workspace_bytes) return set_error("decoder_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
   cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
   const int D = w->embed_dim, Hh = w->num_heads, bf = w->is_bf16, B = c->B, G = c->G, Nm = c->Nm;
+  const int depth = w->depth;
   const int M = (int)ws.M;
   const int Nt = (int)ws.Nt;
   const int mode = c->mem_mode;
   const int mw = mode == M3R_MEM_KV ? 2 * D : D;         // width of a memory row (decoder.py:189,277)
+  if (mode != M3R_MEM_KV) for (int l = 0; l < depth; ++l)
+    if (!w->blocks[l].kv_w || !w->blocks[l].normy_w) return set_error("decoder_forward: memory_mode norm_y / raw needs the unfolded kv_w and the norm_y affine");
   int n_total = 0;
   for (int g = 0; g < G; ++g) n_total += c->groups[g].n_views;
   // make_mem_mask rule (decoder.py:199-204, 291-296): skip own tokens unless rendering or a lone first image
   const bool use_skip = !c->render && (Nm > 0 || n_total > 1);
-  if (!c->render) g_side.init();
-  const bool side = !c->render && g_side.ok;
+  SideStream* sd = c->render ? nullptr : side_streams();
+  if (sd) sd->init();
+  const bool side = sd && sd->ok;
   if (!c->render && Nm > 0 && !c->new_only) {
-    // old memory rows -> output memory tensors (the reference's torch.cat, decoder.py:330); independent of the whole
-    // step, so it runs on a copy stream and is joined at the end
-    cudaStream_t cps = side ? g_side.copy : cs;
-    if (side) g_side.link(cs, cps);
-    for (int l = 0; l < w->depth; ++l) {
+    // old memory rows -> output memory tensors (the reference's torch.cat, decoder.py:330) unless the caller appends in
+    // place (mem_out[l] == mem[l]); independent of the whole step: copy stream, joined at the end
+    cudaStream_t cps = side ? sd->copy : cs;
+    bool linked = false;
+    for (int l = 0; l < depth; ++l) {
       if (!c->mem_out[l]) return set_error("decoder_forward: mem_out[%d] is null", l);
       if (c->mem[l] == c->mem_out[l]) continue;
-      cudaError_t e = cudaMemcpy2DAsync(c->mem_out[l], (size_t)c->mem_out_bstride_rows * mw * 2, c->mem[l],
-                                        (size_t)c->mem_bstride_rows * mw * 2, (size_t)Nm * mw * 2, B,
-                                        cudaMemcpyDeviceToDevice, cps);
+      if (side && !linked) { M3R_TRY(sd->link(cs, cps)); linked = true; }
+      cudaError_t e = cudaSuccess;
+      if (c->mem_bstride_rows == 0 && B > 1) {            // stride-0 (expanded) memory: one source block for every scene
+        for (int bb = 0; bb < B && e == cudaSuccess; ++bb)
+          e = cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->mem_out[l]) + (size_t)bb * c->mem_out_bstride_rows * mw * 2, c->mem[l],
+                              (size_t)Nm * mw * 2, cudaMemcpyDeviceToDevice, cps);
+      } else {
+        e = cudaMemcpy2DAsync(c->mem_out[l], (size_t)c->mem_out_bstride_rows * mw * 2, c->mem[l],
+                              (size_t)c->mem_bstride_rows * mw * 2, (size_t)Nm * mw * 2, B, cudaMemcpyDeviceToDevice, cps);
+      }
       if (e != cudaSuccess) return set_error("decoder_forward: memory copy failed: %s", cudaGetErrorString(e));
     }
   }
 
-  // ---- prologue: projector + image2_embed, RoPE table (decoder.py:168-187, 272-289)
+  // LayerNorm placement: when the [M, D] residual stream fits in one wave of 128x64 tiles, every GEMM that produces it
+  // also emits the normalised rows for its consumer (m3r_gemm_args.norm_out); otherwise a separate affine-free pass runs.
+  static int emit_env = -1;
+  if (emit_env < 0) { const char* e = getenv("M3R_EMIT"); emit_env = (e && e[0] == '0') ? 0 : 1; }
+  const int tiles_m = (M + 127) / 128;
+  const bool emit = emit_env == 1 && D % 64 == 0 && D <= 768 && tiles_m <= 16 && tiles_m * (D / 64) <= num_sms();
+  // residual-stream GEMM: xo = xr + A W^T + b, followed by (or fused with) the normalisation of xo into h16
+  auto res_gemm = [&](const void* A, int64_t lda, const void* W, int K, const float* bias, const float* xr, float* xo,
+                      const float* rowbias, int rb_period, int rb_first, int Mrows, int64_t row_off) -> int {
+    m3r_gemm_args a = {};
+    a.A = A; a.lda = lda; a.W = W; a.ldw = K; a.M = Mrows; a.N = D; a.K = K; a.is_bf16 = bf; a.bias = bias;
+    a.residual = xr ? xr + row_off * D : nullptr; a.ldr = D; a.out = xo + row_off * D; a.ldc = D; a.out_dtype = M3R_OUT_F32;
+    a.rowbias = rowbias; a.rb_period = rb_period; a.rb_first = rb_first; a.w_static = 1;
+    if (emit && Mrows == M) { a.norm_out = ws.h16; a.ldn = D; a.norm_eps = w->ln_eps; }
+    M3R_TRY(m3r_gemm(&a, stream));
+    if (!(emit && Mrows == M) && row_off + Mrows == M)      // (grouped prologue: normalise once, after the last group)
+      M3R_TRY(m3r_normalize16(xo, D, nullptr, 0, 0, 1, w->ln_eps, M, D, ws.h16, D, bf, stream));
+    return 0;
+  };
+
+  // ---- prologue: projector + image2_embed, RoPE table (decoder.py:168-187, 272-289); X_0 -> snap[0] (update) or x (render)
+  float* x0 = c->render ? ws.x : ws.snap;
   for (int g = 0; g < G; ++g) {
     const m3r_dec_group& gr = c->groups[g];
     const int Mg = B * gr.n_views * gr.N;
@@ -242,126 +285,33 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     M3R_TRY(m3r_rope_table(gr.pos, Mg, w->rope_base, w->rope_f0, ws.rope + ws.row0[g] * 64, stream));
     M3R_TRY(m3r_cast16(gr.x_enc, w->enc_dim, Mg, w->enc_dim, ws.enc16 + ws.row0[g] * w->enc_dim, w->enc_dim, bf, stream));
     const int first = (c->is_init && g == 0) ? gr.N : 0;    // rows of view 0 of every scene get no embed at init
-    M3R_TRY(gemm(ws.enc16 + ws.row0[g] * w->enc_dim, w->enc_dim, w->embed_w, w->enc_dim, Mg, D, w->enc_dim, bf, w->embed_b, 0,
-                 nullptr, 0, ws.x + ws.row0[g] * D, D, M3R_OUT_F32, stream, nullptr, 0, 0, w->image2_embed,
-                 gr.n_views * gr.N, first));
+    M3R_TRY(res_gemm(ws.enc16 + ws.row0[g] * w->enc_dim, w->enc_dim, w->embed_w, w->enc_dim, w->embed_b, nullptr, x0,
+                     w->image2_embed, gr.n_views * gr.N, first, Mg, ws.row0[g]));
   }
 
-  float* xcur = ws.x;
-  for (int l = 0; l < w->depth; ++l) {
-    const m3r_dec_block& b = w->blocks[l];
-    float* xin = xcur;                                   // block input X_l
-    float* xout;                                         // where X_{l+1} goes
-    if (!c->render) {
-      // new_mem[l] = X_l must survive (decoder.py:304): blocks ping through the snapshot ring
-      if (l == 0) {
-        M3R_TRY(cudaMemcpyAsync(ws.snap, xin, (size_t)M * D * 4, cudaMemcpyDeviceToDevice, cs) != cudaSuccess ? set_error("memcpy failed") : 0);
-        xin = ws.snap;
-      }
-      xout = (l + 1 < w->depth) ? ws.snap + (int64_t)(l + 1) * M * D : ws.x;
-      // pre-feedback K|V of the new tokens -> second key segment (decoder.py:306, layers.py:81-88); independent of
-      // the self-attention branch until the cross-attention, so it runs on the side stream
-      void* kst = side ? (void*)g_side.s : stream;
-      if (side) g_side.link(cs, g_side.s);
-      M3R_TRY(m3r_layernorm(xin, D, nullptr, 0, b.normy_w, b.normy_b, w->ln_eps, M, D, ws.h16b, D, M3R_OUT_16, bf, kst));
-      for (int g = 0; g < G; ++g) {
-        const m3r_dec_group& gr = c->groups[g];
-        const int Mg = B * gr.n_views * gr.N;
-        M3R_TRY(gemm(ws.h16b + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
-                     ws.kvnew + ws.tok0[g] * 2 * D, 2 * D, M3R_OUT_16, kst, nullptr, 0, 0, nullptr, 1, 0,
-                     gr.n_views * gr.N, Nt));
-      }
-    } else {
-      xout = ws.x;
-    }
-    if (mode != M3R_MEM_KV && Nm > 0) {
-      // memory_mode norm_y / raw: K|V of the stored rows are projected at use (layers.py:92-96); independent of x, so in
-      // update mode it shares the side stream with the new tokens' projection
-      void* mst = (side && !c->render) ? (void*)g_side.s : stream;
-      for (int bm = 0; bm < ws.nbm; ++bm) {
-        const uint16_t* src = reinterpret_cast<const uint16_t*>(c->mem[l]) + (int64_t)bm * c->mem_bstride_rows * D;
-        if (mode == M3R_MEM_RAW) {
-          uint16_t* ln = ws.memln + (int64_t)bm * Nm * D;
-          M3R_TRY(m3r_layernorm16(src, D, b.normy_w, b.normy_b, w->ln_eps, Nm, D, ln, D, bf, mst));
-          src = ln;
-        }
-        M3R_TRY(gemm(src, D, b.kv_w, D, Nm, 2 * D, D, bf, b.kv_b, 0, nullptr, 0, ws.kvmem + (int64_t)bm * Nm * 2 * D, 2 * D,
-                     M3R_OUT_16, mst));
-      }
-    }
-    // ---- self-attention (layers.py:91)
-    M3R_TRY(m3r_layernorm(xin, D, nullptr, 0, b.norm1_w, b.norm1_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
-    M3R_TRY(gemm(ws.h16, D, b.qkv_w, D, M, 3 * D, D, bf, b.qkv_b, 0, nullptr, 0, ws.qkv16, 3 * D, M3R_OUT_16, stream,
-                 ws.rope, 2 * D, M));
-    for (int g = 0; g < G; ++g) {
-      const m3r_dec_group& gr = c->groups[g];
-      uint16_t* qkv = ws.qkv16 + ws.row0[g] * 3 * D;
-      m3r_attn_args at = {};
-      at.Q = qkv; at.ldq = 3 * D;
-      at.K0 = qkv + D; at.V0 = qkv + 2 * D; at.ldk0 = 3 * D; at.kv_bstride0 = gr.N; at.Nk0 = gr.N;
-      at.O = ws.att16 + ws.row0[g] * D; at.ldo = D; at.B = B * gr.n_views; at.H = Hh; at.Nq = gr.N; at.kv_group = 1;
-      at.is_bf16 = bf; at.scale = 0.125f;
-      M3R_TRY(m3r_attention(&at, stream));
-    }
-    // x_tmp = X_l + proj(SA)    (out of place so X_l survives in update mode)
-    float* xt = c->render ? xin : ws.tmp;
-    M3R_TRY(gemm(ws.att16, D, b.proj_w, D, M, D, D, bf, b.proj_b, 0, xin, D, xt, D, M3R_OUT_F32, stream));
-    // ---- memory cross-attention (layers.py:92-97, attention.py:139-149): q = projq(LN2(x)), K|V = memory (+ new)
-    M3R_TRY(m3r_layernorm(xt, D, nullptr, 0, b.norm2_w, b.norm2_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
-    M3R_TRY(gemm(ws.h16, D, b.q_w, D, M, D, D, bf, b.q_b, 0, nullptr, 0, ws.q16, D, M3R_OUT_16, stream));
-    if (side && !c->render) g_side.link(g_side.s, cs);      // join: kvnew is ready
-    for (int g = 0; g < G; ++g) {
-      const m3r_dec_group& gr = c->groups[g];
-      m3r_attn_args at = {};
-      at.Q = ws.q16 + ws.row0[g] * D; at.ldq = D;
-      const uint16_t* mem_l = Nm > 0 ? reinterpret_cast<const uint16_t*>(c->mem[l]) : nullptr;
-      if (Nm > 0) {
-        if (mode == M3R_MEM_KV) {
-          at.K0 = mem_l; at.V0 = mem_l + D; at.ldk0 = 2 * D; at.kv_bstride0 = c->mem_bstride_rows; at.Nk0 = Nm;
-        } else {
-          at.K0 = ws.kvmem; at.V0 = ws.kvmem + D; at.ldk0 = 2 * D; at.kv_bstride0 = ws.nbm > 1 ? Nm : 0; at.Nk0 = Nm;
-        }
-        if (!c->render) { at.K1 = ws.kvnew; at.V1 = ws.kvnew + D; at.ldk1 = 2 * D; at.kv_bstride1 = Nt; at.Nk1 = Nt; }
+  // ---- feedback + memory append (feedback_mechanism.py:39-53, decoder.py:323-330), enqueued on stream `st` once
+  // new_mem[depth-1] (the input of the last block) exists: offset = Mlp(LN_fb(new_mem[-1])); level l < depth-1 stores
+  // K|V(LN_y(new_mem[l] + offset)), the last level K|V(LN_y(new_mem[-1])).
+  auto append_memory = [&](void* st) -> int {
+    const float* off = nullptr;
+    if (w->feedback) {
+      const float* last = ws.snap + (int64_t)(depth - 1) * M * D;
+      M3R_TRY(m3r_normalize16(last, D, nullptr, 0, 0, 1, w->fb_ln_eps, M, D, ws.hfb16, D, bf, st));
+      if (w->feedback == 1) {
+        M3R_TRY(gemm(ws.hfb16, D, w->fb1_w, D, M, 4 * D, D, bf, w->fb1_b, M3R_ACT_GELU, nullptr, 0, ws.mlpfb16, 4 * D, M3R_OUT_16, st));
+        M3R_TRY(gemm(ws.mlpfb16, 4 * D, w->fb2_w, 4 * D, M, D, 4 * D, bf, w->fb2_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, st));
       } else {
-        at.K0 = ws.kvnew; at.V0 = ws.kvnew + D; at.ldk0 = 2 * D; at.kv_bstride0 = Nt; at.Nk0 = Nt;   // first call: only new tokens
+        M3R_TRY(gemm(ws.hfb16, D, w->fb1_w, D, M, D, D, bf, w->fb1_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, st));
       }
-      at.O = ws.att16 + ws.row0[g] * D; at.ldo = D; at.B = B * gr.n_views; at.H = Hh; at.Nq = gr.N;
-      at.kv_group = gr.n_views; at.is_bf16 = bf; at.scale = 0.125f;
-      if (use_skip) { at.skip_lo = Nm + (int)ws.tok0[g]; at.skip_step = gr.N; at.skip_len = gr.N; }
-      M3R_TRY(m3r_attention(&at, stream));
+      off = ws.off;
     }
-    M3R_TRY(gemm(ws.att16, D, b.cproj_w, D, M, D, D, bf, b.cproj_b, 0, xt, D, xt, D, M3R_OUT_F32, stream));
-    // ---- MLP (layers.py:98)
-    M3R_TRY(m3r_layernorm(xt, D, nullptr, 0, b.norm3_w, b.norm3_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
-    M3R_TRY(gemm(ws.h16, D, b.fc1_w, D, M, w->mlp_hidden, D, bf, b.fc1_b, M3R_ACT_GELU, nullptr, 0, ws.mlp16, w->mlp_hidden,
-                 M3R_OUT_16, stream));
-    M3R_TRY(gemm(ws.mlp16, w->mlp_hidden, b.fc2_w, w->mlp_hidden, M, D, w->mlp_hidden, bf, b.fc2_b, 0, xt, D, xout, D,
-                 M3R_OUT_F32, stream));
-    xcur = xout;
-  }
-
-  // ---- feedback offset (feedback_mechanism.py:39-53): needed by the post-feedback K|V of every level but the last
-  const float* off = nullptr;
-  if (!c->render && w->feedback) {
-    const float* last = ws.snap + (int64_t)(w->depth - 1) * M * D;      // new_mem[-1] = input of the last block
-    M3R_TRY(m3r_layernorm(last, D, nullptr, 0, w->fbn_w, w->fbn_b, w->fb_ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
-    if (w->feedback == 1) {
-      M3R_TRY(gemm(ws.h16, D, w->fb1_w, D, M, 4 * D, D, bf, w->fb1_b, M3R_ACT_GELU, nullptr, 0, ws.mlp16, 4 * D, M3R_OUT_16, stream));
-      M3R_TRY(gemm(ws.mlp16, 4 * D, w->fb2_w, 4 * D, M, D, 4 * D, bf, w->fb2_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, stream));
-    } else {
-      M3R_TRY(gemm(ws.h16, D, w->fb1_w, D, M, D, D, bf, w->fb1_b, 0, nullptr, 0, ws.off, D, M3R_OUT_F32, stream));
-    }
-    off = ws.off;
-  }
-  // post-feedback K|V rows appended to the memory (decoder.py:323-330): levels [l0, l1) on stream `st`
-  auto post_feedback = [&](int l0, int l1, void* st, uint16_t* hbuf) -> int {
-    for (int l = l0; l < l1; ++l) {
-      const m3r_dec_block& b = w->blocks[l];
-      uint16_t* mo = reinterpret_cast<uint16_t*>(c->mem_out[l]);
-      if (!mo) return set_error("decoder_forward: mem_out[%d] is null", l);
-      const float* add = (off && l < w->depth - 1) ? off : nullptr;        // the last level gets no offset
-      if (mode != M3R_MEM_KV) {
-        // norm_y stores LN_y(new_mem + off), raw stores new_mem + off (layers.py:81-86), D-wide rows
+    for (int l = 0; l < depth; ++l) if (!c->mem_out[l]) return set_error("decoder_forward: mem_out[%d] is null", l);
+    if (mode != M3R_MEM_KV) {
+      // norm_y stores LN_y(new_mem + off), raw stores new_mem + off (layers.py:81-86), D-wide rows
+      for (int l = 0; l < depth; ++l) {
+        const m3r_dec_block& b = w->blocks[l];
+        uint16_t* mo = reinterpret_cast<uint16_t*>(c->mem_out[l]);
+        const float* add = (off && l < depth - 1) ? off : nullptr;
         for (int g = 0; g < G; ++g) {
           const m3r_dec_group& gr = c->groups[g];
           const int rows = gr.n_views * gr.N;
@@ -376,30 +326,134 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
               M3R_TRY(m3r_add_cast16(xs, D, as, D, rows, D, dst, D, bf, st));
           }
         }
-        continue;
       }
-      M3R_TRY(m3r_layernorm(ws.snap + (int64_t)l * M * D, D, add, D, b.normy_w, b.normy_b, w->ln_eps, M, D, hbuf, D, M3R_OUT_16, bf, st));
-      for (int g = 0; g < G; ++g) {
-        const m3r_dec_group& gr = c->groups[g];
-        const int Mg = B * gr.n_views * gr.N;
-        void* peers[M3R_MAX_PEERS];
-        for (int r = 0; r < c->n_peers; ++r)
-          peers[r] = reinterpret_cast<uint16_t*>(c->peer_mem[r * w->depth + l]) + ws.tok0[g] * 2 * D;
-        M3R_TRY(gemm(hbuf + ws.row0[g] * D, D, b.kv_w, D, Mg, 2 * D, D, bf, b.kv_b, 0, nullptr, 0,
-                     mo + ((int64_t)(c->new_only ? 0 : Nm) + ws.tok0[g]) * 2 * D, 2 * D, M3R_OUT_16, st, nullptr, 0, 0, nullptr, 1, 0,
-                     gr.n_views * gr.N, c->mem_out_bstride_rows, c->n_peers, peers));
+      return 0;
+    }
+    // kv: ONE normalisation over the [depth * M] rows of all levels, then the K|V projections of all levels as one
+    // grouped GEMM (weights = rows [3D,5D) of each block's stacked a_w) whose epilogue writes the stored rows - and, in the
+    // multi-GPU schedule, every rank's copy of them - in place
+    M3R_TRY(m3r_normalize16(ws.snap, D, off, D, (depth - 1) * M, M, w->ln_eps, depth * M, D, ws.hpost16, D, bf, st));
+    bool stacked = depth <= M3R_MAX_GROUPS;
+    for (int l = 1; l < depth && stacked; ++l)
+      stacked = w->blocks[l].a_w == reinterpret_cast<const uint16_t*>(w->blocks[0].a_w) + (int64_t)l * 5 * D * D &&
+                w->blocks[l].a_b == w->blocks[0].a_b + (int64_t)l * 5 * D;
+    for (int g = 0; g < G; ++g) {
+      const m3r_dec_group& gr = c->groups[g];
+      const int Mg = B * gr.n_views * gr.N;
+      m3r_gemm_args a = {};
+      a.lda = D; a.ldw = D; a.M = Mg; a.N = 2 * D; a.K = D; a.is_bf16 = bf; a.ldc = 2 * D; a.out_dtype = M3R_OUT_16;
+      a.rows_per_batch = gr.n_views * gr.N; a.batch_stride_rows = c->mem_out_bstride_rows; a.w_static = 1; a.n_peer_out = c->n_peers;
+      const int64_t orow = (int64_t)(c->new_only ? 0 : Nm) + ws.tok0[g];
+      if (stacked && G == 1) {
+        m3r_gemm_group grp = {};
+        grp.groups = depth; grp.w_group_rows = 5 * D; grp.bias_group = 5 * D;
+        a.A = ws.hpost16; a.W = reinterpret_cast<const uint16_t*>(w->blocks[0].a_w) + (int64_t)3 * D * D; a.bias = w->blocks[0].a_b + 3 * D;
+        for (int l = 0; l < depth; ++l) {
+          grp.out[l] = reinterpret_cast<uint16_t*>(c->mem_out[l]) + orow * 2 * D;
+          for (int r = 0; r < c->n_peers; ++r)
+            grp.peer_out[l * M3R_MAX_PEERS + r] = reinterpret_cast<uint16_t*>(c->peer_mem[r * depth + l]) + ws.tok0[g] * 2 * D;
+        }
+        M3R_TRY(m3r_gemm_grouped(&a, &grp, st));
+      } else {
+        for (int l = 0; l < depth; ++l) {
+          const m3r_dec_block& b = w->blocks[l];
+          a.A = ws.hpost16 + ((int64_t)l * M + ws.row0[g]) * D;
+          a.W = reinterpret_cast<const uint16_t*>(b.a_w) + (int64_t)3 * D * D; a.bias = b.a_b + 3 * D;
+          a.out = reinterpret_cast<uint16_t*>(c->mem_out[l]) + orow * 2 * D;
+          for (int r = 0; r < c->n_peers; ++r) a.peer_out[r] = reinterpret_cast<uint16_t*>(c->peer_mem[r * depth + l]) + ws.tok0[g] * 2 * D;
+          M3R_TRY(m3r_gemm(&a, st));
+        }
       }
     }
     return 0;
   };
-  const int l_split = side ? w->depth / 2 : 0;
-  if (!c->render && side) {
-    g_side.link(cs, g_side.s);                                 // fork: `off` and the snapshots are ready
-    M3R_TRY(post_feedback(0, l_split, g_side.s, ws.h16b));
+  bool appended = false;
+  auto maybe_append = [&](int ready_level) -> int {      // called when X_{ready_level} has been enqueued
+    if (c->render || appended || ready_level != depth - 1) return 0;
+    appended = true;
+    if (!side) return 0;                                  // without a side stream the append runs after the head
+    M3R_TRY(sd->link(cs, sd->s));
+    return append_memory(sd->s);
+  };
+  M3R_TRY(maybe_append(0));
+
+  for (int l = 0; l < depth; ++l) {
+    const m3r_dec_block& b = w->blocks[l];
+    float* xin = c->render ? ws.x : ws.snap + (int64_t)l * M * D;                     // block input X_l (= new_mem[l], decoder.py:304)
+    float* xout = c->render ? ws.x : (l + 1 < depth ? ws.snap + (int64_t)(l + 1) * M * D : ws.x);
+    float* xt = c->render ? xin : ws.tmp;                                             // X_l must survive in update mode
+    const int ldb = ws.merged ? 5 * D : 3 * D;
+    // ---- h16 = n(X_l): first GEMM = self-attention q|k|v (RoPE on q,k) [+ pre-feedback K|V of the new tokens, the second
+    // key segment of the cross-attention (decoder.py:306, layers.py:81-88)]
+    M3R_TRY(gemm(ws.h16, D, b.a_w, D, M, ldb, D, bf, b.a_b, 0, nullptr, 0, ws.big16, ldb, M3R_OUT_16, stream, ws.rope, 2 * D, M));
+    if (!c->render && !ws.merged) {
+      for (int g = 0; g < G; ++g) {
+        const m3r_dec_group& gr = c->groups[g];
+        const int Mg = B * gr.n_views * gr.N;
+        M3R_TRY(gemm(ws.h16 + ws.row0[g] * D, D, reinterpret_cast<const uint16_t*>(b.a_w) + (int64_t)3 * D * D, D, Mg, 2 * D, D, bf, b.a_b + 3 * D, 0,
+                     nullptr, 0, ws.kvnew + ws.tok0[g] * 2 * D, 2 * D, M3R_OUT_16, stream, nullptr, 0, 0, nullptr, 1, 0,
+                     gr.n_views * gr.N, Nt));
+      }
+    }
+    if (mode != M3R_MEM_KV && Nm > 0) {
+      // memory_mode norm_y / raw: K|V of the stored rows are projected at use (layers.py:92-96)
+      for (int bm = 0; bm < ws.nbm; ++bm) {
+        const uint16_t* src = reinterpret_cast<const uint16_t*>(c->mem[l]) + (int64_t)bm * c->mem_bstride_rows * D;
+        if (mode == M3R_MEM_RAW) {
+          uint16_t* ln = ws.memln + (int64_t)bm * Nm * D;
+          M3R_TRY(m3r_layernorm16(src, D, b.normy_w, b.normy_b, w->ln_eps, Nm, D, ln, D, bf, stream));
+          src = ln;
+        }
+        M3R_TRY(gemm(src, D, b.kv_w, D, Nm, 2 * D, D, bf, b.kv_b, 0, nullptr, 0, ws.kvmem + (int64_t)bm * Nm * 2 * D, 2 * D,
+                     M3R_OUT_16, stream));
+      }
+    }
+    // ---- self-attention (layers.py:91)
+    for (int g = 0; g < G; ++g) {
+      const m3r_dec_group& gr = c->groups[g];
+      uint16_t* qkv = ws.big16 + ws.row0[g] * ldb;
+      m3r_attn_args at = {};
+      at.Q = qkv; at.ldq = ldb;
+      at.K0 = qkv + D; at.V0 = qkv + 2 * D; at.ldk0 = ldb; at.kv_bstride0 = gr.N; at.Nk0 = gr.N;
+      at.O = ws.att16 + ws.row0[g] * D; at.ldo = D; at.B = B * gr.n_views; at.H = Hh; at.Nq = gr.N; at.kv_group = 1;
+      at.is_bf16 = bf; at.scale = 0.125f;
+      M3R_TRY(m3r_attention(&at, stream));
+    }
+    // x_t = X_l + proj(SA), h16 = n(x_t)
+    M3R_TRY(res_gemm(ws.att16, D, b.proj_w, D, b.proj_b, xin, xt, nullptr, 1, 0, M, 0));
+    // ---- memory cross-attention (layers.py:92-97, attention.py:139-149): q = projq(LN2(x)), K|V = memory (+ new)
+    M3R_TRY(gemm(ws.h16, D, b.q_w, D, M, D, D, bf, b.q_b, 0, nullptr, 0, ws.q16, D, M3R_OUT_16, stream));
+    for (int g = 0; g < G; ++g) {
+      const m3r_dec_group& gr = c->groups[g];
+      m3r_attn_args at = {};
+      at.Q = ws.q16 + ws.row0[g] * D; at.ldq = D;
+      const uint16_t* mem_l = Nm > 0 ? reinterpret_cast<const uint16_t*>(c->mem[l]) : nullptr;
+      const uint16_t* kn = ws.merged ? ws.big16 + 3 * D : ws.kvnew;       // this call's K|V rows
+      const int64_t ldn = ws.merged ? 5 * D : 2 * D;
+      if (Nm > 0) {
+        if (mode == M3R_MEM_KV) {
+          at.K0 = mem_l; at.V0 = mem_l + D; at.ldk0 = 2 * D; at.kv_bstride0 = c->mem_bstride_rows; at.Nk0 = Nm;
+        } else {
+          at.K0 = ws.kvmem; at.V0 = ws.kvmem + D; at.ldk0 = 2 * D; at.kv_bstride0 = ws.nbm > 1 ? Nm : 0; at.Nk0 = Nm;
+        }
+        if (!c->render) { at.K1 = kn; at.V1 = kn + D; at.ldk1 = ldn; at.kv_bstride1 = Nt; at.Nk1 = Nt; }
+      } else {
+        at.K0 = kn; at.V0 = kn + D; at.ldk0 = ldn; at.kv_bstride0 = Nt; at.Nk0 = Nt;   // first call: only new tokens
+      }
+      at.O = ws.att16 + ws.row0[g] * D; at.ldo = D; at.B = B * gr.n_views; at.H = Hh; at.Nq = gr.N;
+      at.kv_group = gr.n_views; at.is_bf16 = bf; at.scale = 0.125f;
+      if (use_skip) { at.skip_lo = Nm + (int)ws.tok0[g]; at.skip_step = gr.N; at.skip_len = gr.N; }
+      M3R_TRY(m3r_attention(&at, stream));
+    }
+    M3R_TRY(res_gemm(ws.att16, D, b.cproj_w, D, b.cproj_b, xt, xt, nullptr, 1, 0, M, 0));
+    // ---- MLP (layers.py:98)
+    M3R_TRY(gemm(ws.h16, D, b.fc1_w, D, M, w->mlp_hidden, D, bf, b.fc1_b, M3R_ACT_GELU, nullptr, 0, ws.mlp16, w->mlp_hidden,
+                 M3R_OUT_16, stream));
+    M3R_TRY(res_gemm(ws.mlp16, w->mlp_hidden, b.fc2_w, w->mlp_hidden, b.fc2_b, xt, xout, nullptr, 1, 0, M, 0));
+    M3R_TRY(maybe_append(l + 1));
   }
 
-  // ---- prediction head (decoder.py:149-156, head.py:69-72): LN -> Linear(768->1792) fp32 -> pixel shuffle
-  M3R_TRY(m3r_layernorm(xcur, D, nullptr, 0, w->normd_w, w->normd_b, w->ln_eps, M, D, ws.h16, D, M3R_OUT_16, bf, stream));
+  // ---- prediction head (decoder.py:149-156, head.py:69-72): LN (emitted by the last fc2) -> Linear(768->1792) fp32 -> pixel shuffle
   M3R_TRY(gemm(ws.h16, D, w->head_w, D, M, w->out_dim, D, bf, w->head_b, 0, nullptr, 0, ws.headout, w->out_dim, M3R_OUT_F32, stream));
   for (int g = 0; g < G; ++g) {
     const m3r_dec_group& gr = c->groups[g];
@@ -407,10 +461,10 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   }
 
   if (!c->render) {
-    M3R_TRY(post_feedback(l_split, w->depth, stream, ws.h16));
+    if (!side) M3R_TRY(append_memory(stream));
     if (side) {
-      g_side.link(g_side.s, cs);                               // join the side stream
-      if (Nm > 0 && !c->new_only) g_side.link(g_side.copy, cs);  // and the old-memory copies
+      M3R_TRY(sd->link(sd->s, cs));                                // join the side stream
+      if (Nm > 0 && !c->new_only) M3R_TRY(sd->link(sd->copy, cs));  // and the old-memory copies
     }
   }
   return 0;

@@ -164,6 +164,60 @@ extern "C" int m3r_ipc_close(void* ptr) {
   return e == cudaSuccess ? 0 : m3r::set_error("ipc_close: %s", cudaGetErrorString(e));
 }
 
+// ---- device-side flag barrier for the multi-GPU schedule (engine/sharded.py): every rank owns a uint32 slot in every
+// rank's flag array (peer-mapped memory).  m3r_peer_signal, enqueued after the kernels whose peer stores must be visible,
+// publishes an epoch number into its slot on all ranks; m3r_peer_wait spins (on the GPU, never on the host) until the slots
+// of the ranks in `rank_mask` have reached the epoch.  Stream order + system-scope release / acquire make the K|V rows
+// that the GEMM epilogues stored into this GPU's memory visible to the kernels enqueued after the wait.
+namespace m3r {
+struct SlotList { unsigned int* p[M3R_MAX_PEERS]; };
+__global__ void peer_signal_kernel(SlotList slots, int n, unsigned int value) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // the producing kernels of this stream have completed
+  if ((int)threadIdx.x < n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(slots.p[threadIdx.x]), "r"(value) : "memory");
+  }
+}
+__global__ void peer_wait_kernel(const unsigned int* flags, unsigned int rank_mask, unsigned int value) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const unsigned int r = threadIdx.x;
+  if (r < 32 && ((rank_mask >> r) & 1u)) {
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+      if ((int)(v - value) >= 0) break;
+      if (clock64() - t0 > 60000000000ll) __trap();            // ~30 s: a peer died; fail the launch instead of hanging the box
+      __nanosleep(100);
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+}
+}  // namespace m3r
+
+extern "C" int m3r_peer_signal(void* const* flag_slots, int32_t n, uint32_t value, void* stream) {
+  using namespace m3r;
+  if (!flag_slots || n < 1 || n > M3R_MAX_PEERS) return set_error("peer_signal: 1..%d slots", M3R_MAX_PEERS);
+  SlotList sl;
+  for (int i = 0; i < M3R_MAX_PEERS; ++i) sl.p[i] = i < n ? reinterpret_cast<unsigned int*>(flag_slots[i]) : nullptr;
+  cudaError_t e = launch_pdl(peer_signal_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream), sl, (int)n, (unsigned int)value);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("peer_signal launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+extern "C" int m3r_peer_wait(const void* local_flags, uint32_t rank_mask, uint32_t value, void* stream) {
+  using namespace m3r;
+  if (!local_flags) return set_error("peer_wait: null pointer");
+  cudaError_t e = launch_pdl(peer_wait_kernel, dim3(1), dim3(32), 0, reinterpret_cast<cudaStream_t>(stream),
+                             reinterpret_cast<const unsigned int*>(local_flags), (unsigned int)rank_mask, (unsigned int)value);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error("peer_wait launch: %s", cudaGetErrorString(e));
+  count_launch();
+  return 0;
+}
+
 // Debug hook (tools/trace_attn.py, tools/trace_gemm.py): device buffer that the next attention / GEMM launches fill with
 // %globaltimer stamps (64 / 16 uint64 per CTA); nullptr switches it off.  The stamps are compiled in only with -DM3R_TRACE
 // (M3R_TRACE=1 python -m must3r_b200.build): they cost registers in the hot loops.

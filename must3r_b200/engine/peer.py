@@ -21,16 +21,25 @@ class _RawCudaBuffer:
 
 class PeerArena:
     """`nbytes` of device memory on every rank; ``local`` is a uint8 torch view of this rank's block,
-    ``ptrs[r]`` the address of rank r's block as seen from this process (own block: the local address)."""
+    ``ptrs[r]`` the address of rank r's block as seen from this process (own block: the local address).
+    Behind the block sit `FLAG_BYTES` of barrier flags: a uint32 slot per rank (m3r_peer_signal / m3r_peer_wait)."""
+
+    FLAG_BYTES = 256
 
     def __init__(self, nbytes: int, device: torch.device):
         lib = _lib.lib()
         rank, world = dist.get_rank(), dist.get_world_size()
         self.nbytes, self.device, self._opened = nbytes, device, []
+        self.rank, self.world, self.epoch = rank, world, 0
+        nbytes_al = (nbytes + 255) // 256 * 256
         p = C.c_void_p()
-        _lib.check(lib.m3r_peer_alloc(nbytes, C.byref(p)), "peer_alloc")
+        _lib.check(lib.m3r_peer_alloc(nbytes_al + self.FLAG_BYTES, C.byref(p)), "peer_alloc")
         self.ptr = p.value
-        self.local = torch.as_tensor(_RawCudaBuffer(self.ptr, nbytes), device=device)
+        self.flag_off = nbytes_al
+        whole = torch.as_tensor(_RawCudaBuffer(self.ptr, nbytes_al + self.FLAG_BYTES), device=device)
+        whole[nbytes_al:].zero_()
+        torch.cuda.synchronize(device)
+        self.local = whole[:nbytes]
         handle = (C.c_uint8 * 64)()
         _lib.check(lib.m3r_ipc_export(C.c_void_p(self.ptr), handle), "ipc_export")
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
@@ -47,6 +56,25 @@ class PeerArena:
             self.ptrs.append(q.value)
             self._opened.append(q.value)
         dist.barrier()
+        self._slots = (C.c_void_p * world)(*[self.ptrs[r] + self.flag_off + 4 * rank for r in range(world)])
+
+    # ---- device-side barrier: no host synchronisation, the launch thread keeps enqueueing
+    def signal(self, stream_ptr):
+        """Publish the next epoch to every rank once the work enqueued so far on the stream has completed."""
+        self.epoch += 1
+        _lib.check(_lib.lib().m3r_peer_signal(self._slots, self.world, self.epoch, stream_ptr), "peer_signal")
+
+    def skip_epoch(self):
+        """A round this rank sits out: keep the epoch counters of all ranks in step."""
+        self.epoch += 1
+
+    def wait(self, ranks, stream_ptr):
+        """Work enqueued after this sees everything the given ranks stored before signalling the current epoch."""
+        mask = 0
+        for r in ranks:
+            mask |= 1 << r
+        if mask:
+            _lib.check(_lib.lib().m3r_peer_wait(C.c_void_p(self.ptr + self.flag_off), mask, self.epoch, stream_ptr), "peer_wait")
 
     def close(self):
         lib = _lib.lib()

@@ -1,7 +1,7 @@
 """Multi-GPU schedule of the hot path (the reference has no multi-GPU inference at all).
 
-One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests).  Every rank holds the same
-number V of views of ONE scene (global view id = rank * V + i):
+One process per GPU (torch.distributed, NCCL over NVLink; gloo in the CPU tests).  Rank r holds view_counts[r]
+views of ONE scene (global view order is rank-major):
 
   1. encoder: each rank encodes its own V views (independent units, no collective);
   2. memory init: rank 0 runs the reference's 2-view initialisation on its views 0,1 (decoder.py:280-285) and the
@@ -14,9 +14,13 @@ number V of views of ONE scene (global view id = rank * V + i):
   4. render: each rank renders its V views against the final replicated memory (no collective).
 
 On CUDA with the must3r_b200 decoder the gather is FUSED into the producing GEMM: the memory buffers live in
-peer-visible device memory (`engine/peer.py`, CUDA IPC) and the epilogue of the post-feedback K|V projection stores each
-16-bit tile into every rank's buffer over NVLink while the kernel is still computing other tiles; a barrier per round
-replaces the all-gather (M3R_FUSED_GATHER=0 selects the NCCL all-gather path, which is also what gloo/CPU runs use).
+peer-visible device memory (`engine/peer.py`, CUDA IPC) and the epilogue of the post-feedback K|V projection (one grouped
+GEMM over all decoder levels) stores each 16-bit tile into every rank's buffer over NVLink while the kernel is still
+computing other tiles.  Rounds are ordered by a DEVICE-side flag barrier (m3r_peer_signal / m3r_peer_wait: the producers
+publish an epoch into every rank's flag array, consumers spin on their own copy): no host synchronisation and no
+collective on the data path, so the launch thread enqueues round k+1 while round k runs.  M3R_FUSED_GATHER=0 selects the
+NCCL all-gather path, which is also what gloo/CPU runs use.  Ranks may hold different numbers of views (`view_counts`,
+e.g. 100 views ceil-split over 8 GPUs): a rank without a view in a round only waits.
 
 With world_size 1 the schedule degenerates to the reference chain (init 2 views, then 1 view per step).
 The oracle for world_size > 1 is composed from single-process decoder calls only (tests/test_sharded_cpu.py).
@@ -65,12 +69,17 @@ def _all_gather(packed: torch.Tensor, world: int) -> torch.Tensor:
 @torch.no_grad()
 def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Tensor,
                       post_process_function: Optional[Callable] = None, device=None, to_host: bool = False,
-                      render_bs: Optional[int] = None, return_mem: bool = False):
-    """imgs [V,3,H,W], true_shape [V,2]: this rank's views (same V and image size on every rank).
+                      render_bs: Optional[int] = None, return_mem: bool = False, view_counts: Optional[List[int]] = None):
+    """imgs [V,3,H,W], true_shape [V,2]: this rank's views of ONE scene (same image size on every rank).
+    `view_counts[r]` = number of views held by rank r (default: the same V everywhere); global view order is rank-major.
     Returns the list of this rank's V rendered results (dicts if post_process_function is given)."""
     rank, world = _world()
     device = device or imgs.device
     V = imgs.shape[0]
+    counts = list(view_counts) if view_counts is not None else [V] * world
+    assert len(counts) == world and counts[rank] == V, "view_counts must list every rank's number of views"
+    assert counts[0] >= 1, "rank 0 holds the first views of the scene (memory initialisation)"
+    total = sum(counts)
     hw = None
     if not true_shape.is_cuda:                                 # host copy of (H, W): spares a device sync per decoder call
         assert bool((true_shape == true_shape[:1]).all()), "all views of a rank must share one true_shape"
@@ -93,6 +102,7 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
     mem_vals: Optional[List[torch.Tensor]] = None              # depth x [1, cap, mem_D] pre-allocated
     labels = None
     n_mem_views = 0
+    cap = total * N
 
     def current_mem():
         if n_mem_views == 0:
@@ -105,7 +115,6 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
         nonlocal mem_vals, labels, n_mem_views
         depth, mem_D = gathered.shape[1], gathered.shape[3]
         if mem_vals is None:
-            cap = world * V * N
             mem_vals = [torch.empty((1, cap, mem_D), dtype=gathered.dtype, device=gathered.device) for _ in range(depth)]
             labels = torch.empty((1, cap), dtype=torch.int64, device=gathered.device)
         sel = [r for r in range(world) if flags[r]]
@@ -120,16 +129,23 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
         labels[0, Nm:Nm + cnt] = lab.repeat_interleave(N)
         n_mem_views += len(sel) * n_each
 
-    n_init = min(2, V)
+    n_init = min(2, counts[0])
+    rounds = max(counts)
+
+    def round_flags(s):
+        """ranks that store view s in round s (rank 0's first n_init views went in with the initialisation)"""
+        return [s < counts[r] and not (r == 0 and s < n_init) for r in range(world)]
+
     fused = (world > 1 and x.is_cuda and hasattr(decoder, "update_tokens_to_peers")
              and getattr(decoder, "memory_mode", "kv") == "kv"      # the GEMM epilogue that stores to peers is the K|V one
              and os.environ.get("M3R_FUSED_GATHER", "1") != "0")
     arena = None
     if fused:
-        # ---- fused GEMM -> all-gather: every rank's memory buffers are peer-mapped; producers store into all of them
+        # ---- fused GEMM -> all-gather: every rank's memory buffers are peer-mapped; producers store into all of them.
+        # Ordering is kept on the GPUs: a flag barrier per round (PeerArena.signal / wait), the host never blocks.
         from .peer import PeerArena
+        from ..model.common import stream_ptr
         depth, mem_D, dt = decoder.depth, 2 * decoder.embed_dim, decoder.memory_dtype()
-        cap = world * V * N
         esz = torch.empty((), dtype=dt).element_size()
         akey = (depth * cap * mem_D * esz, str(x.device))
         arena = None if return_mem else _ARENA_CACHE.get(akey)
@@ -139,28 +155,40 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
                 _ARENA_CACHE[akey] = arena
         mem_vals = [arena.local[l * cap * mem_D * esz:(l + 1) * cap * mem_D * esz].view(dt).view(1, cap, mem_D) for l in range(depth)]
         labels = torch.empty((1, cap), dtype=torch.int64, device=x.device)
+        sp = stream_ptr(x.device)
 
         def dests(row):       # peer_ptrs[r][l] for new tokens starting at memory row `row`
             return [[arena.ptrs[r] + (l * cap + row) * mem_D * esz for l in range(depth)] for r in range(world)]
 
-        def commit(n_views_added):
+        def commit(participants, n_views_added):
+            """The participants' rows of this round have been enqueued: they signal, everyone waits for them (on the GPU)."""
             nonlocal n_mem_views
             Nm = n_mem_views * N
             cnt = n_views_added * N
             labels[0, Nm:Nm + cnt] = torch.arange(n_mem_views, n_mem_views + n_views_added, device=labels.device).repeat_interleave(N)
             n_mem_views += n_views_added
-            dist.barrier()        # every rank's peer stores have landed before anyone reads the new rows
+            if rank in participants:
+                arena.signal(sp)
+            else:
+                arena.skip_epoch()
+            arena.wait(participants, sp)
 
+        # entry barrier: a cached arena may still be read by a slower rank's render of the previous call
+        arena.signal(sp)
+        arena.wait(range(world), sp)
         if rank == 0:
             decoder.update_tokens_to_peers(x[None, :n_init], pos[None, :n_init], true_shape[None, :n_init], None, dests(0))
-        commit(n_init)
-        for s in range(V):
-            flags = [not (r == 0 and s < n_init) for r in range(world)]
+        commit([0], n_init)
+        for s in range(rounds):
+            flags = round_flags(s)
+            part = [r for r in range(world) if flags[r]]
+            if not part:
+                continue
             if flags[rank]:
                 slot = sum(flags[:rank])
                 decoder.update_tokens_to_peers(x[None, s:s + 1], pos[None, s:s + 1], true_shape[None, s:s + 1], current_mem(),
                                                dests((n_mem_views + slot) * N))
-            commit(sum(flags))
+            commit(part, len(part))
 
     # ---- 2. init on rank 0 (views 0,1); every rank runs the same gather so the memory is replicated
     if not fused:
@@ -184,13 +212,12 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
                [r == 0 for r in range(world)], n_init)
 
         # ---- 3. update rounds: one view per rank per round, one all-gather per round
-        for s in range(V):
-            mine = not (rank == 0 and s < n_init)
-            flags = [not (r == 0 and s < n_init) for r in range(world)]
+        for s in range(rounds):
+            flags = round_flags(s)
             if not any(flags):
                 continue
             # ranks that sit a round out still take part in the collective (with a dummy payload)
-            if mine:
+            if flags[rank]:
                 toks, _ = _new_tokens(decoder, x[None, s:s + 1], pos[None, s:s + 1], true_shape[None, s:s + 1], current_mem())
                 packed = torch.stack([t[0] for t in toks], 0)                              # [depth, N, mem_D]
             else:
@@ -201,7 +228,7 @@ def inference_sharded(encoder, decoder, imgs: torch.Tensor, true_shape: torch.Te
     # ---- 4. render this rank's views against the replicated memory
     mem = current_mem()
     outs = []
-    bs = render_bs or V
+    bs = render_bs or max(V, 1)
     for lo in range(0, V, bs):
         _, pm = decoder(x[None, lo:lo + bs], pos[None, lo:lo + bs], true_shape[None, lo:lo + bs], mem, render=True)
         pm = pm[0]

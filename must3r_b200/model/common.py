@@ -28,8 +28,8 @@ class EncoderWeights(C.Structure):
 
 class DecBlock(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
-        "norm1_w", "norm1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "norm2_w", "norm2_b", "normy_w", "normy_b",
-        "q_w", "q_b", "kv_w", "kv_b", "cproj_w", "cproj_b", "norm3_w", "norm3_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+        "a_w", "a_b", "proj_w", "proj_b", "q_w", "q_b", "cproj_w", "cproj_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b",
+        "normy_w", "normy_b", "kv_w", "kv_b")]
 
 
 class DecoderWeights(C.Structure):
@@ -39,9 +39,8 @@ class DecoderWeights(C.Structure):
                 ("is_bf16", C.c_int32), ("feedback", C.c_int32),
                 ("embed_w", C.c_void_p), ("embed_b", C.c_void_p), ("image2_embed", C.c_void_p),
                 ("blocks", C.POINTER(DecBlock)),
-                ("fbn_w", C.c_void_p), ("fbn_b", C.c_void_p), ("fb1_w", C.c_void_p), ("fb1_b", C.c_void_p),
-                ("fb2_w", C.c_void_p), ("fb2_b", C.c_void_p),
-                ("normd_w", C.c_void_p), ("normd_b", C.c_void_p), ("head_w", C.c_void_p), ("head_b", C.c_void_p)]
+                ("fb1_w", C.c_void_p), ("fb1_b", C.c_void_p), ("fb2_w", C.c_void_p), ("fb2_b", C.c_void_p),
+                ("head_w", C.c_void_p), ("head_b", C.c_void_p)]
 
 
 class DecGroup(C.Structure):
@@ -160,6 +159,15 @@ class WeightPack:
         self.keep.append(x)
         return x.data_ptr()
 
+    def folded(self, lin_w: torch.Tensor, lin_b: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+        """Linear(LayerNorm(x)) with the affine moved into the Linear: W' = W diag(gamma), b' = b + W beta (fp32 maths;
+        W' is rounded to the 16-bit operand format once, exactly like W would be).  -> (W' fp32 [N,K], b' fp32 [N])"""
+        w = lin_w.detach().float()
+        b = w @ beta.detach().float()
+        if lin_b is not None:
+            b = b + lin_b.detach().float()
+        return w * gamma.detach().float()[None, :], b
+
     def vec(self, t: Optional[torch.Tensor]) -> Optional[int]:
         if t is None:
             return None
@@ -181,5 +189,6 @@ def workspace(device: torch.device, nbytes: int, tag: str) -> torch.Tensor:
     return buf
 
 
-def stream_ptr() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(device=None) -> C.c_void_p:
+    """The caller's current stream ON THE TENSORS' DEVICE (not on whatever device happens to be current)."""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

@@ -122,25 +122,40 @@ class MUSt3R(nn.Module):
         return super().load_state_dict(*a, **k)
 
     def _packed(self, dtype):
+        """Kernel-format weights (include/must3r_b200.h m3r_decoder_weights): every LayerNorm affine folded into the Linear
+        that consumes it; per block the self-attention qkv and the memory K|V projection stacked into one [5D, D] matrix, all
+        blocks in ONE contiguous [depth, 5D, D] array (so the memory append is one grouped GEMM)."""
         key = (dtype, str(self.norm_dec.weight.device))
         if self._pack is None or self._pack[0] != key:
             p = cm.WeightPack()
+            D = self.embed_dim
             blocks = (cm.DecBlock * self.depth)()
+            a_w_all = torch.empty((self.depth, 5 * D, D), dtype=dtype, device=self.norm_dec.weight.device)
+            a_b_all = torch.empty((self.depth, 5 * D), dtype=torch.float32, device=self.norm_dec.weight.device)
+            p.keep += [a_w_all, a_b_all]
+            esz = a_w_all.element_size()
             for i, b in enumerate(self.blocks_dec):
                 e = blocks[i]
-                e.norm1_w, e.norm1_b = p.vec(b.norm1.weight), p.vec(b.norm1.bias)
-                e.qkv_w, e.qkv_b = p.mat(b.attn.qkv.weight, dtype), p.vec(b.attn.qkv.bias)
-                e.proj_w, e.proj_b = p.mat(b.attn.proj.weight, dtype), p.vec(b.attn.proj.bias)
-                e.norm2_w, e.norm2_b = p.vec(b.norm2.weight), p.vec(b.norm2.bias)
-                e.normy_w, e.normy_b = p.vec(b.norm_y.weight), p.vec(b.norm_y.bias)
                 ca = b.cross_attn
-                e.q_w, e.q_b = p.mat(ca.projq.weight, dtype), p.vec(ca.projq.bias)
-                e.kv_w = p.mat(torch.cat([ca.projk.weight, ca.projv.weight], 0), dtype)
-                e.kv_b = p.vec(torch.cat([ca.projk.bias, ca.projv.bias], 0))
+                wq, bq = p.folded(b.attn.qkv.weight, b.attn.qkv.bias, b.norm1.weight, b.norm1.bias)
+                kv_w = torch.cat([ca.projk.weight, ca.projv.weight], 0)
+                kv_b = torch.cat([ca.projk.bias, ca.projv.bias], 0)
+                wk, bk = p.folded(kv_w, kv_b, b.norm_y.weight, b.norm_y.bias)
+                a_w_all[i, :3 * D] = wq.to(dtype)
+                a_w_all[i, 3 * D:] = wk.to(dtype)
+                a_b_all[i, :3 * D] = bq
+                a_b_all[i, 3 * D:] = bk
+                e.a_w = a_w_all.data_ptr() + i * 5 * D * D * esz
+                e.a_b = a_b_all.data_ptr() + i * 5 * D * 4
+                e.proj_w, e.proj_b = p.mat(b.attn.proj.weight, dtype), p.vec(b.attn.proj.bias)
+                wq2, bq2 = p.folded(ca.projq.weight, ca.projq.bias, b.norm2.weight, b.norm2.bias)
+                e.q_w, e.q_b = p.mat(wq2, dtype), p.vec(bq2)
                 e.cproj_w, e.cproj_b = p.mat(ca.proj.weight, dtype), p.vec(ca.proj.bias)
-                e.norm3_w, e.norm3_b = p.vec(b.norm3.weight), p.vec(b.norm3.bias)
-                e.fc1_w, e.fc1_b = p.mat(b.mlp.fc1.weight, dtype), p.vec(b.mlp.fc1.bias)
+                w1, b1 = p.folded(b.mlp.fc1.weight, b.mlp.fc1.bias, b.norm3.weight, b.norm3.bias)
+                e.fc1_w, e.fc1_b = p.mat(w1, dtype), p.vec(b1)
                 e.fc2_w, e.fc2_b = p.mat(b.mlp.fc2.weight, dtype), p.vec(b.mlp.fc2.bias)
+                e.normy_w, e.normy_b = p.vec(b.norm_y.weight), p.vec(b.norm_y.bias)
+                e.kv_w, e.kv_b = p.mat(kv_w, dtype), p.vec(kv_b)          # memory_mode norm_y / raw: projected at use
             w = cm.DecoderWeights()
             w.enc_dim, w.embed_dim, w.depth, w.num_heads = self.enc_embed_dim, self.embed_dim, self.depth, self.attn_num_heads
             w.mlp_hidden, w.out_dim = self.mlp_hidden, self.output_dim
@@ -151,17 +166,17 @@ class MUSt3R(nn.Module):
             w.blocks = blocks
             if self.feedback_type == 'single_mlp':
                 w.feedback, w.fb_ln_eps = 1, self.feedback_norm.eps
-                w.fbn_w, w.fbn_b = p.vec(self.feedback_norm.weight), p.vec(self.feedback_norm.bias)
-                w.fb1_w, w.fb1_b = p.mat(self.feedback_layer.fc1.weight, dtype), p.vec(self.feedback_layer.fc1.bias)
+                f1, fb = p.folded(self.feedback_layer.fc1.weight, self.feedback_layer.fc1.bias, self.feedback_norm.weight, self.feedback_norm.bias)
+                w.fb1_w, w.fb1_b = p.mat(f1, dtype), p.vec(fb)
                 w.fb2_w, w.fb2_b = p.mat(self.feedback_layer.fc2.weight, dtype), p.vec(self.feedback_layer.fc2.bias)
             elif self.feedback_type == 'single_linear':
                 w.feedback, w.fb_ln_eps = 2, self.feedback_norm.eps
-                w.fbn_w, w.fbn_b = p.vec(self.feedback_norm.weight), p.vec(self.feedback_norm.bias)
-                w.fb1_w, w.fb1_b = p.mat(self.feedback_layer.weight, dtype), p.vec(self.feedback_layer.bias)
+                f1, fb = p.folded(self.feedback_layer.weight, self.feedback_layer.bias, self.feedback_norm.weight, self.feedback_norm.bias)
+                w.fb1_w, w.fb1_b = p.mat(f1, dtype), p.vec(fb)
             else:
                 w.feedback, w.fb_ln_eps = 0, 1e-5
-            w.normd_w, w.normd_b = p.vec(self.norm_dec.weight), p.vec(self.norm_dec.bias)
-            w.head_w, w.head_b = p.mat(self.head_dec.proj.weight, dtype), p.vec(self.head_dec.proj.bias)
+            hw, hb = p.folded(self.head_dec.proj.weight, self.head_dec.proj.bias, self.norm_dec.weight, self.norm_dec.bias)
+            w.head_w, w.head_b = p.mat(hw, dtype), p.vec(hb)
             self._pack = (key, w, blocks, p)
         return self._pack[1]
 
@@ -284,9 +299,10 @@ class MUSt3R(nn.Module):
                 call.n_peers, call.peer_mem = len(_peer_ptrs), flat
                 keep.append(flat)
         nbytes = lib.m3r_decoder_workspace_bytes(C.byref(w), C.byref(call))
-        ws = cm.workspace(dev, nbytes, "dec")
-        _lib.check(lib.m3r_decoder_forward(C.byref(w), C.byref(call), C.c_void_p(ws.data_ptr()), ws.numel(), cm.stream_ptr()),
-                   "decoder_forward")
+        with torch.cuda.device(dev):           # the library keys its per-device state (side streams, scratch) on the current device
+            ws = cm.workspace(dev, nbytes, "dec")
+            _lib.check(lib.m3r_decoder_forward(C.byref(w), C.byref(call), C.c_void_p(ws.data_ptr()), ws.numel(), cm.stream_ptr(dev)),
+                       "decoder_forward")
         if _new_only:
             return None, outs, new_mem
         if render:

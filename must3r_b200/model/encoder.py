@@ -153,8 +153,9 @@ class Dust3rEncoder(nn.Module):
         pos1 = self._positions(gh, gw, img.device)
         out = torch.empty((V, N, self.embed_dim), dtype=torch.float32, device=img.device)
         nbytes = lib.m3r_encoder_workspace_bytes(C.byref(w), V, H, W)
-        ws = cm.workspace(img.device, nbytes, "enc")
-        _lib.check(lib.m3r_encoder_forward(C.byref(w), C.c_void_p(img.data_ptr()), V, H, W, C.c_void_p(pos1.data_ptr()),
-                                           C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
-                                           cm.stream_ptr()), "encoder_forward")
+        with torch.cuda.device(img.device):
+            ws = cm.workspace(img.device, nbytes, "enc")
+            _lib.check(lib.m3r_encoder_forward(C.byref(w), C.c_void_p(img.data_ptr()), V, H, W, C.c_void_p(pos1.data_ptr()),
+                                               C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                               cm.stream_ptr(img.device)), "encoder_forward")
         return out, pos1.view(1, N, 2).expand(V, -1, -1).clone()

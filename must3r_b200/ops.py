@@ -17,7 +17,7 @@ F16 = {torch.float16: 0, torch.bfloat16: 1}
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)      # ops are called with the tensors' device current
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -34,7 +34,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            residual: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rb_period: int = 1,
            rb_first: int = 0, rope_tab: Optional[torch.Tensor] = None, rope_cols: int = 0,
            out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
-           rows_per_batch: int = 0, batch_stride_rows: int = 0, peer_ptrs=(), w_static: bool = False) -> torch.Tensor:
+           rows_per_batch: int = 0, batch_stride_rows: int = 0, peer_ptrs=(), w_static: bool = False,
+           norm_out: Optional[torch.Tensor] = None, norm_eps: float = 1e-6) -> torch.Tensor:
     """out = act(a @ w.T + bias [+rope]) [+ residual]; a [M,K] and w [N,K] fp16/bf16, fp32 accumulate.
     peer_ptrs: device pointers (ints) that receive a copy of the 16-bit output (fused GEMM -> all-gather).
     w_static: w is a weight that the previous launch on this stream does not write (lets the kernel fetch it early)."""
@@ -72,7 +73,49 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     args.n_peer_out = len(peer_ptrs)
     for i, ptr in enumerate(peer_ptrs):
         args.peer_out[i] = ptr
+    if norm_out is not None:
+        # LayerNorm emitted by the producing GEMM: norm_out = affine-free LayerNorm of the fp32 output rows, 16-bit
+        assert norm_out.dtype == a.dtype and norm_out.shape == (M, N) and norm_out.stride(1) == 1
+        args.norm_out, args.ldn, args.norm_eps = norm_out.data_ptr(), norm_out.stride(0), norm_eps
     _lib.check(_lib.lib().m3r_gemm(C.byref(args), _stream()), "gemm")
+    return out
+
+
+def linear_grouped(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], outs, *, peer_ptrs=None) -> None:
+    """`groups` GEMMs of one shape in a single launch: a [G, M, K], w [G, N, K] (any row stride between groups),
+    bias [G, N] or None, outs = list of G 16-bit tensors [M, N] (one common row stride)."""
+    _req_cuda(a, w)
+    G, M, K = a.shape
+    N = w.shape[1]
+    assert a.is_contiguous() and w.stride(2) == 1 and w.stride(1) == K and len(outs) == G
+    args = _lib.GemmArgs()
+    args.A, args.lda, args.W, args.ldw = a.data_ptr(), K, w.data_ptr(), K
+    args.M, args.N, args.K, args.is_bf16 = M, N, K, F16[a.dtype]
+    args.bias = bias.data_ptr() if bias is not None else None
+    args.ldc, args.out_dtype = outs[0].stride(0), 0 if outs[0].dtype == torch.float32 else 1
+    grp = _lib.GemmGroup()
+    grp.groups, grp.w_group_rows = G, w.stride(0) // K
+    grp.bias_group = bias.stride(0) if bias is not None else 0
+    for g in range(G):
+        assert outs[g].stride(0) == outs[0].stride(0) and outs[g].stride(1) == 1
+        grp.out[g] = outs[g].data_ptr()
+    if peer_ptrs:
+        args.n_peer_out = len(peer_ptrs[0])
+        for g in range(G):
+            for r, ptr in enumerate(peer_ptrs[g]):
+                grp.peer_out[g * 8 + r] = ptr
+    _lib.check(_lib.lib().m3r_gemm_grouped(C.byref(args), C.byref(grp), _stream()), "gemm_grouped")
+
+
+def normalize16(x: torch.Tensor, eps: float, dtype: torch.dtype, add: Optional[torch.Tensor] = None, add_rows: int = 0) -> torch.Tensor:
+    """Affine-free LayerNorm of fp32 rows -> 16-bit; `add` [P, D] is added to rows < add_rows with period P."""
+    _req_cuda(x)
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.stride(1) == 1
+    M, D = x.shape
+    out = torch.empty((M, D), device=x.device, dtype=dtype)
+    _lib.check(_lib.lib().m3r_normalize16(_p(x), x.stride(0), _p(add), add.stride(0) if add is not None else 0,
+                                          add_rows, add.shape[0] if add is not None else 1, eps, M, D, _p(out), out.stride(0),
+                                          F16[dtype], _stream()), "normalize16")
     return out
 
 

@@ -176,6 +176,38 @@ def full_model_golden():
     np.savez_compressed(os.path.join(HERE, "full_model_digest.npz"), **out)
 
 
+def chain_golden():
+    """The benchmarked schedules, end to end through the reference ENGINE (engine/inference.py:370 inference_multi_ar, the
+    call bench.py times): C3 = 20 views 512x384, mem_batches [2]+[1]*18, render all 20; C2 = 10 views 224x224, [2]+[1]*8,
+    render all 10.  CPU fp32, SDPA branch, PyTorch RoPE fallback.  Digests only (strided samples + moments)."""
+    out = {}
+    for tag, (V, H, W, size) in {"c2": (10, 224, 224, 224), "c3": (20, 384, 512, 512)}.items():
+        enc, dec = build_ref(dict(img_size=(size, size)),
+                             dict(img_size=(size, size), feedback_type="single_mlp", memory_mode="kv",
+                                  landscape_only=False), seed=0)
+        imgs, ts = syn.synthetic_views(V, H, W, seed=2)
+        views, tss = list(imgs.unbind(0)), list(ts.unbind(0))
+        ids = [torch.tensor(i) for i in range(V)]
+        raw = lambda pm: {"raw": pm}  # noqa: E731
+        mem, pm0, pm = ref_engine.inference_multi_ar(enc, dec, views, ids, tss, [2] + [1] * (V - 2), max_bs=None,
+                                                     post_process_function=raw, device="cpu", return_mem=True)
+        raw_r = torch.stack([d["raw"] for d in pm])                       # [V,H,W,7] rendered
+        raw_0 = torch.stack([d["raw"] for d in pm0])                      # first-pass predictions of the update calls
+        post = ref_engine.postprocess(raw_r, ActivationType.NORM_EXP)
+        out[f"{tag}.raw_render"] = digest(raw_r, 65536)
+        out[f"{tag}.raw_first"] = digest(raw_0, 65536)
+        out[f"{tag}.pts3d"] = digest(post["pts3d"], 32768)
+        out[f"{tag}.pts3d_local"] = digest(post["pts3d_local"], 32768)
+        out[f"{tag}.conf"] = digest(post["conf"], 32768)
+        out[f"{tag}.raw_view_last"] = digest(raw_r[-1], 16384)            # the view that saw the longest chain
+        out[f"{tag}.mem0"] = digest(mem[0][0], 16384)
+        out[f"{tag}.mem11"] = digest(mem[0][11], 16384)
+        out[f"{tag}.labels"] = mem[1][:, ::193].numpy()
+        out[f"{tag}.tail"] = np.array(mem[2:], dtype=np.int64)
+        print(tag, "done", flush=True)
+    np.savez_compressed(os.path.join(HERE, "chain_digest.npz"), **out)
+
+
 def engine_golden():
     """Engine schedulers (engine/inference.py) driven with the tiny reference model."""
     out = {}
@@ -261,3 +293,5 @@ if __name__ == "__main__":
         engine_golden()
     if "full" in which:
         full_model_golden()
+    if "chain" in which:
+        chain_golden()

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
         assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
-    assert lib.m3r_abi_version() == 3
+    assert lib.m3r_abi_version() == 4
 
 
 def test_ctypes_structs_match_the_c_layout(tmp_path):
@@ -37,13 +37,13 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
     from must3r_b200 import _lib
     from must3r_b200.model import common as cm
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include "must3r_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
-                    'sizeof(m3r_gemm_args),sizeof(m3r_attn_args),sizeof(m3r_enc_block),sizeof(m3r_encoder_weights),'
+    prog.write_text('#include <stdio.h>\n#include "must3r_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+                    'sizeof(m3r_gemm_group),sizeof(m3r_gemm_args),sizeof(m3r_attn_args),sizeof(m3r_enc_block),sizeof(m3r_encoder_weights),'
                     'sizeof(m3r_dec_block),sizeof(m3r_decoder_weights),sizeof(m3r_dec_group),sizeof(m3r_decoder_call));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    got = [C.sizeof(t) for t in (_lib.GemmArgs, _lib.AttnArgs, cm.EncBlock, cm.EncoderWeights, cm.DecBlock,
+    got = [C.sizeof(t) for t in (_lib.GemmGroup, _lib.GemmArgs, _lib.AttnArgs, cm.EncBlock, cm.EncoderWeights, cm.DecBlock,
                                  cm.DecoderWeights, cm.DecGroup, cm.DecoderCall)]
     assert got == sizes
 

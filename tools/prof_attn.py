@@ -88,6 +88,24 @@ if "sweep" in which:
         res.sort()
         print(f"sweep {name:20s} default {ms0*1e3:7.1f} us | best " + "  ".join(f"qt{q_}s{s_}:{m*1e3:.1f}" for m, q_, s_ in res[:5]), flush=True)
 
+if "longmem" in which:       # one-view update cross-attention against long memories (C4: up to 100 views, C5: ~360)
+    for M_ in (20, 50, 100, 200):
+        B, H, Nq, Nk = 1, 12, 768, 768 * M_
+        D = H * 64
+        q = torch.randn(B * Nq, D, device="cuda").to(dt)
+        kv = torch.randn(B * Nk, 2 * D, device="cuda").to(dt)
+        res = []
+        for qt in (1, 2):
+            for sp in (2, 4, 6, 8, 12, 16, 24):
+                os.environ["M3R_ATTN_QT"] = str(qt); os.environ["M3R_ATTN_SPLITS"] = str(sp)
+                ms = timeit(lambda: ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk), iters=5)
+                res.append((ms, qt, sp))
+        os.environ.pop("M3R_ATTN_QT"); os.environ.pop("M3R_ATTN_SPLITS")
+        ms0 = timeit(lambda: ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk), iters=5)
+        res.sort()
+        fl = 4.0 * B * H * Nq * Nk * 64
+        print(f"longmem 1v x M={M_:3d} default {ms0*1e3:8.1f} us ({fl/ms0/1e9:6.1f} TF/s) | best " + "  ".join(f"qt{q_}s{s_}:{m*1e3:.1f}us({fl/m/1e9:.0f})" for m, q_, s_ in res[:4]), flush=True)
+
 if "small" in which:
     import os as _os
     for name, (M, N, K) in {"dec qkv 1v": (768, 2304, 768), "dec proj 1v": (768, 768, 768), "dec kv 1v": (768, 1536, 768),
