@@ -541,6 +541,7 @@ def main():
     records = {}
     if not args.no_records:
         def rec(tag, mk, steps, warm, with_parity):
+            torch.cuda.empty_cache()
             j, m = mk()
             t = timed(j, steps, warm)
             r = {"workload": CONFIGS[tag]["label"], "views": m["views"], "ms_per_job": round(t, 3), "views_per_s": round(m["views"] / (t / 1e3), 2),

@@ -559,11 +559,12 @@ template <bool BF16, int QT, int POLY, int CS>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CUtensorMap& tmV0, const CUtensorMap& tmK1,
                        const CUtensorMap& tmV1, const AttnParams& p, int B, cudaStream_t s) {
   using Cfg = AttnCfg<QT, CS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};               // per device (function attributes are per context)
+  int dev = 0; cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<BF16, QT, POLY, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev] = true;
   }
   dim3 grid((p.Nq + QT * AT_BM - 1) / (QT * AT_BM), p.H, B * p.splits);
   cudaError_t e = launch_pdl(attn_kernel<BF16, QT, POLY, CS>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, tmQ, tmK0, tmV0, tmK1, tmV1, p);
@@ -573,9 +574,10 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CU
   return 0;
 }
 
-// scratch for the split path, grown on demand (stream-ordered)
-static float* g_split_buf = nullptr;
-static size_t g_split_cap = 0;
+// scratch for the split path, grown on demand (stream-ordered); one per device.  Launches that split must stay on one
+// stream per device at a time (the decoder's side streams never run split attention).
+struct SplitScratch { float* buf = nullptr; size_t cap = 0; };
+static SplitScratch g_split[64];
 
 }  // namespace m3r
 
@@ -652,16 +654,19 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     const size_t n_cnt = (size_t)a->B * a->H * ((a->Nq + AT_BM - 1) / AT_BM);
     if (n_cnt > CNT) return set_error("attention: too many (batch, head, tile) groups for the split path");
     const size_t need = CNT + (size_t)splits * n_cnt * AT_BM * (HD + 2);     // partial O + (m, l), padded to whole query tiles
-    if (need > g_split_cap) {
-      if (g_split_buf) cudaFreeAsync(g_split_buf, cs);
-      g_split_buf = nullptr; g_split_cap = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return set_error("attention: bad current device");
+    SplitScratch& sc = g_split[dev];
+    if (need > sc.cap) {
+      if (sc.buf) cudaFreeAsync(sc.buf, cs);
+      sc.buf = nullptr; sc.cap = 0;
       const size_t cap = need + need / 2;
-      if (cudaMallocAsync(&g_split_buf, cap * sizeof(float), cs) != cudaSuccess) return set_error("attention: split scratch allocation failed");
-      if (cudaMemsetAsync(g_split_buf, 0, CNT * sizeof(int), cs) != cudaSuccess) return set_error("attention: counter memset failed");
-      g_split_cap = cap;
+      if (cudaMallocAsync(&sc.buf, cap * sizeof(float), cs) != cudaSuccess) return set_error("attention: split scratch allocation failed");
+      if (cudaMemsetAsync(sc.buf, 0, CNT * sizeof(int), cs) != cudaSuccess) return set_error("attention: counter memset failed");
+      sc.cap = cap;
     }
-    p.split_cnt = reinterpret_cast<int*>(g_split_buf);
-    p.part_o = g_split_buf + CNT;
+    p.split_cnt = reinterpret_cast<int*>(sc.buf);
+    p.part_o = sc.buf + CNT;
     p.part_ml = p.part_o + (size_t)splits * n_cnt * AT_BM * HD;
   }
   {

@@ -326,8 +326,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (!row_ok) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
-        } else {
-          epilogue_store(p, p.out, p.peer_out, v, orow, n0 + c_lo * 32);
         }
         // two-pass statistics of the thread's 32 values, combined across the row's 2 * tiles_n partials with Chan's
         // formula (as accurate as a two-pass LayerNorm over the whole row)
@@ -345,8 +343,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __threadfence();
         asm volatile("bar.sync 1, 256;" ::: "memory");
         unsigned int* cnt = p.sync + 2 * tm;
+        if (warp == 2 && lane == 0) atom_add_release_u32(cnt, 1u);
+        // the fp32 residual stream goes out while the other CTAs of the row block arrive (its 32 KB per CTA would otherwise
+        // sit in front of the fence above)
+        if (row_ok) epilogue_store(p, p.out, p.peer_out, v, orow, n0 + c_lo * 32);
         if (warp == 2 && lane == 0) {
-          atom_add_release_u32(cnt, 1u);
           unsigned int spins = 0;
           while (ld_acquire_u32(cnt) < (unsigned int)tiles_n) { if (++spins > (1u << 26)) __trap(); }
         }

@@ -199,7 +199,20 @@ def inference_multi_ar_batch(encoder, decoder, imgs, true_shape, mem=None, verbo
                              encoder_precomputed_features=None, preserve_gpu_mem=False,
                              post_process_function=lambda x: {'pts3d': x}, device=None, render=False,
                              viser_server=None):
-    """One decoder call over already-stacked aspect-ratio groups (engine/inference.py:168-202)."""
+    """One decoder call over already-stacked aspect-ratio groups (engine/inference.py:168-202).  With preserve_gpu_mem
+    the results are host tensors and, like the reference's `.to('cpu')`, complete when the call returns."""
+    out = _multi_ar_batch(encoder, decoder, imgs, true_shape, mem, verbose, encoder_precomputed_features, preserve_gpu_mem,
+                          post_process_function, device, render, viser_server)
+    _sync_host_copies()
+    return out
+
+
+def _multi_ar_batch(encoder, decoder, imgs, true_shape, mem=None, verbose=False,
+                    encoder_precomputed_features=None, preserve_gpu_mem=False,
+                    post_process_function=lambda x: {'pts3d': x}, device=None, render=False,
+                    viser_server=None):
+    """inference_multi_ar_batch without the final wait for the asynchronous device->host copies: the schedulers below keep
+    enqueueing decoder steps while results stream back and call _sync_host_copies() before handing anything out."""
     device = device or true_shape.device
     outdevice = "cpu" if preserve_gpu_mem else device
     if encoder_precomputed_features is None:
@@ -275,6 +288,34 @@ def _shadow_after_call(mem_before, new_mem, idx_st, x_st):
     return new_mem
 
 
+def _arena_of(mem_values):
+    """The growable backing store of a memory produced by the CUDA decoder (model/decoder.py MemArena), or None."""
+    a = getattr(mem_values[0], "_m3r_arena", None) if len(mem_values) else None
+    if a is None:
+        return None
+    from ..model.decoder import MemArena
+    a = MemArena.of(mem_values)
+    return a if (a is not None and a.tail == mem_values[0].shape[1]) else None      # only the latest version may be edited in place
+
+
+def _release_tail(mem):
+    """The engine discards the memory a decoder call returned and keeps `mem` (refinement passes): give the rows appended
+    behind `mem` back, so that the next call on `mem` appends in place again."""
+    if mem is None:
+        return
+    a = getattr(mem[0][0], "_m3r_arena", None)
+    if a is not None:
+        from ..model.decoder import MemArena
+        if MemArena.of(mem[0]) is a and a.tail >= mem[0][0].shape[1]:
+            a.tail = mem[0][0].shape[1]
+
+
+def _reserve(decoder, n_tokens=0, growth=0.0):
+    fn = getattr(decoder, "reserve_memory", None)
+    if fn is not None:
+        fn(n_tokens, growth)
+
+
 def _remove_from_mem(mem_values, mem_labels, idx):
     """Drop every token labelled idx (engine/inference.py:205-213)."""
     sh = _host_labels(mem_labels)
@@ -286,9 +327,27 @@ def _remove_from_mem(mem_values, mem_labels, idx):
     runs = _runs(keep)
     if len(runs) == 1 and runs[0] == (0, sh.shape[0]):
         return mem_values, mem_labels
+    arena = _arena_of(mem_values)
     if len(runs) <= 1 and (not runs or runs[0][0] == 0):
         stop = runs[0][1] if runs else 0                       # the dropped tokens are the tail: prefix views, no copy
-        values, labels = [v[:, :stop] for v in mem_values], mem_labels[:, :stop]
+        if arena is not None:
+            arena.tail = stop                                  # ... and the next decoder call appends right behind them
+            values = arena.views(stop)
+        else:
+            values = [v[:, :stop] for v in mem_values]
+        labels = mem_labels[:, :stop]
+    elif arena is not None:
+        # compaction inside the growable buffers: only the rows behind the hole move (through a scratch copy: source and
+        # destination overlap), the memory keeps its storage and the next decoder call appends in place
+        pos = 0
+        for a, b in runs:
+            if a != pos:
+                for buf in arena.bufs:
+                    buf[:, pos:pos + (b - a)] = buf[:, a:b].clone()
+            pos += b - a
+        arena.tail = pos
+        values = arena.views(pos)
+        labels = torch.cat([mem_labels[:, a:b] for a, b in runs], dim=1)
     else:
         values = [torch.cat([v[:, a:b] for a, b in runs], dim=1) for v in mem_values]
         labels = torch.cat([mem_labels[:, a:b] for a, b in runs], dim=1)
@@ -381,6 +440,7 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
     custom_callbacks = (viser_server is not None or is_keyframe_function is not _default_is_keyframe
                         or scene_state_update_function is not _default_scene_state_update)
     window = deque()
+    _reserve(decoder, 0, 1.5)                  # CUDA decoder: memory buffers grow geometrically, updates append in place
     for _ in range(num_refinements_iterations + 1):
         window = deque()
         for step in range(len(bounds) - 1):
@@ -390,7 +450,7 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
             ts_st, idx_st, x_st, pos_st, img_st = stack_views(ts_i, [x_i, pos_i, imgs_i], max_bs=max_bs)
             n_before = get_Nmem(mem)
             mem_prev = mem
-            new_mem, res = inference_multi_ar_batch(encoder, decoder, img_st, ts_st, mem, verbose=verbose,
+            new_mem, res = _multi_ar_batch(encoder, decoder, img_st, ts_st, mem, verbose=verbose,
                                                     encoder_precomputed_features=(x_st, pos_st),
                                                     preserve_gpu_mem=preserve_gpu_mem,
                                                     post_process_function=post_process_function, device=device,
@@ -439,6 +499,7 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
             gone = window.popleft()
             if gone not in keyframes:
                 mem[0], mem[1] = _remove_from_mem(mem[0], mem[1], label_of[gone])
+    _reserve(decoder)
     _sync_host_copies()
     return (_compact_storage(mem), first_pass) if return_mem else first_pass
 
@@ -460,6 +521,12 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
         bounds = [0] + np.cumsum(mem_batches).tolist()
         first_pass = [None] * bounds[-1]
         label_of = {}
+        # CUDA decoder: size the memory buffers once for the whole schedule, every update then appends in place
+        known = [v for v in x[:bounds[-1]] if v is not None]
+        if len(known) == bounds[-1]:
+            _reserve(decoder, sum(int(v.shape[-2]) for v in known), 0.0)
+        else:
+            _reserve(decoder, 0, 1.5)
         for _ in range(num_refinements_iterations + 1):
             for step in range(len(bounds) - 1):
                 lo, hi = bounds[step], bounds[step + 1]
@@ -467,7 +534,7 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
                 x_i, pos_i = _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device)
                 ts_st, idx_st, x_st, pos_st, img_st = stack_views(ts_i, [x_i, pos_i, imgs_i], max_bs=max_bs)
                 refresh = all(int(v) in label_of for v in ids_i)     # all views already stored: refinement step
-                new_mem, res = inference_multi_ar_batch(encoder, decoder, img_st, ts_st, mem, verbose=verbose,
+                new_mem, res = _multi_ar_batch(encoder, decoder, img_st, ts_st, mem, verbose=verbose,
                                                         encoder_precomputed_features=(x_st, pos_st),
                                                         preserve_gpu_mem=preserve_gpu_mem,
                                                         post_process_function=post_process_function, device=device,
@@ -482,6 +549,7 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
                             continue                                  # reference image: left as is
                         _update_in_mem(mem[0], new_mem[0], mem[1], new_mem[1], old, new_labels[j])
                     del new_mem
+                    _release_tail(mem)
                 else:
                     mem = new_mem
                     for j, vid in enumerate(ids_i):
@@ -491,6 +559,7 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
                 if viser_server is not None:
                     _sync_host_copies()
                     viser_server.set_views(ids_i, imgs_i, res, [True] * len(imgs_i))
+        _reserve(decoder)
     else:
         first_pass, mem = None, precomputed_mem
 
@@ -508,7 +577,7 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
     rendered = []
     for xs, ps, ts, ims, ids in zip(x_st, pos_st, ts_st, img_st, id_st):
         feats = None if (xs is None or ps is None) else ([xs], [ps])
-        _, out = inference_multi_ar_batch(encoder, decoder, [ims], [ts], mem, verbose=verbose,
+        _, out = _multi_ar_batch(encoder, decoder, [ims], [ts], mem, verbose=verbose,
                                           encoder_precomputed_features=feats, preserve_gpu_mem=preserve_gpu_mem,
                                           post_process_function=post_process_function, device=device, render=True,
                                           viser_server=viser_server)

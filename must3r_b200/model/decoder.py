@@ -20,6 +20,36 @@ from . import common as cm
 MEMORY_MODES = ['norm_y', 'kv', 'raw']
 
 
+class MemArena:
+    """Backing store of a memory that can grow in place: per level one [B, cap, mem_D] buffer, of which the first `tail`
+    rows are handed out.  The memory tensors of the tuple are prefix views `buf[:, :rows]` tagged with their arena; an
+    update call whose input memory is the LATEST version (rows == tail) and fits writes its new rows behind it instead of
+    re-creating the reference's `torch.cat` (must3r/model/decoder.py:330).  Older versions stay valid (rows are only ever
+    appended); a call on an older version, or one that does not fit, gets a fresh arena and a copy, exactly as before."""
+
+    __slots__ = ("bufs", "cap", "tail")
+
+    def __init__(self, bufs, cap):
+        self.bufs, self.cap, self.tail = bufs, cap, 0
+
+    def views(self, rows):
+        out = [b[:, :rows] for b in self.bufs]
+        for v in out:
+            v._m3r_arena = self
+        return out
+
+    @staticmethod
+    def of(mem_vals):
+        """The arena behind a list of memory tensors, or None (foreign tensors, copies, re-sliced views)."""
+        a = getattr(mem_vals[0], "_m3r_arena", None) if len(mem_vals) else None
+        if a is None or len(a.bufs) != len(mem_vals):
+            return None
+        for m, b in zip(mem_vals, a.bufs):
+            if getattr(m, "_m3r_arena", None) is not a or m.data_ptr() != b.data_ptr() or m.shape[1] > a.cap or m.stride(0) != b.stride(0):
+                return None
+        return a
+
+
 class _CachedDecoderBlock(nn.Module):
     """Key names of must3r/model/blocks/layers.py:57-79."""
 
@@ -93,6 +123,14 @@ class MUSt3R(nn.Module):
             nn.init.constant_(self.feedback_layer.bias, 0)
             nn.init.constant_(self.feedback_layer.weight, 0)
         self._pack = None
+        self._reserve_tokens = 0
+        self._growth = 0.0
+
+    def reserve_memory(self, n_tokens: int = 0, growth: float = 0.0):
+        """Hint for the memory tensors this decoder allocates from now on: room for `n_tokens` rows per scene and / or
+        geometric over-allocation by `growth` (e.g. 1.5), so that the following update calls append their rows in place
+        (no O(Nmem) copy per call).  `reserve_memory()` restores exact-size allocation (the default)."""
+        self._reserve_tokens, self._growth = int(n_tokens), float(growth)
 
     def memory_dtype(self):
         """dtype of the K|V memory tensors this decoder produces (the current 16-bit operand format)."""
@@ -285,11 +323,23 @@ class MUSt3R(nn.Module):
         new_mem = None
         if not render:
             rows = Nt if _new_only else Nm + Nt
-            new_mem = [torch.empty((B, rows, mem_D), dtype=dtype, device=dev) for _ in range(self.depth)]
+            if _new_only:
+                new_mem = [torch.empty((B, rows, mem_D), dtype=dtype, device=dev) for _ in range(self.depth)]
+                cap = rows
+            else:
+                # append in place when the input is the latest version of an arena with room left (mem_out[l] == mem[l]:
+                # the library then copies nothing); otherwise a fresh arena (exact size unless reserve_memory asked for more)
+                arena = MemArena.of(mv) if Nm > 0 else None
+                if arena is None or arena.tail != Nm or Nm + Nt > arena.cap:
+                    cap = max(rows, self._reserve_tokens, int(rows * self._growth))
+                    arena = MemArena([torch.empty((B, cap, mem_D), dtype=dtype, device=dev) for _ in range(self.depth)], cap)
+                cap = arena.cap
+                new_mem = arena.views(rows)
+                arena.tail = rows
             for l in range(self.depth):
                 out_ptrs[l] = new_mem[l].data_ptr()
             call.mem_out = out_ptrs
-            call.mem_out_bstride_rows = rows
+            call.mem_out_bstride_rows = cap
             call.new_only = 1 if _new_only else 0
             if _peer_ptrs:
                 flat = (C.c_void_p * (len(_peer_ptrs) * self.depth))()

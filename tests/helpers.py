@@ -34,7 +34,7 @@ def full_oracle(size, seed=0):
             orc.OracleDecoder(syn.decoder_state_dict(seed), dcfg))
 
 
-def digest(t, max_elems=4096):
+def digest(t, max_elems=4096):  # same sampling as tests/golden/make_golden.py
     f = t.detach().float().flatten().cpu()
     step = max(1, f.numel() // max_elems)
     return np.concatenate([f[::step][:max_elems].numpy(),

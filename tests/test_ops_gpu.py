@@ -329,7 +329,7 @@ def test_unpatchify_and_postprocess():
 
 def test_errors_are_loud():
     a = torch.zeros(4, 96, device="cuda", dtype=torch.float16)
-    with pytest.raises(RuntimeError, match="multiples of 64"):
+    with pytest.raises(RuntimeError, match="multiple of 32 and K"):
         ops.linear(a, torch.zeros(64, 96, device="cuda", dtype=torch.float16))
     with pytest.raises(RuntimeError):
         ops.linear(a.cpu(), a.cpu())

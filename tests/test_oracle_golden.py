@@ -145,3 +145,22 @@ def test_full_size_digest(tag, H, W, size):
     assert np.array_equal(mem[1][:, ::97].numpy(), g[f"{tag}.labels"])
     _, pm = dec(x[None], pos[None], ts[None], mem, render=True)
     assert rel(digest(pm), g[f"{tag}.pm_render"]) < 5e-5
+
+
+def test_oracle_reproduces_c2_chain_golden():
+    """The benchmarked C2 schedule (10 views 224x224, [2]+[1]*8, render 10) through must3r_b200.engine with the oracle
+    model, against the digest of the UNMODIFIED reference engine's run (tests/golden/chain_digest.npz): pins the oracle
+    AND the engine's scheduling on a full-size chain (the 512x384 / 20-view twin is checked on the GPU only: minutes of CPU)."""
+    from must3r_b200 import engine
+    from helpers import full_oracle, digest
+    g = load_golden("chain_digest.npz")
+    enc, dec = full_oracle(224, 0)
+    imgs, ts = syn.synthetic_views(10, 224, 224, seed=2)
+    views, tss, ids = list(imgs.unbind(0)), list(ts.unbind(0)), [torch.tensor(i) for i in range(10)]
+    mem, pm0, pm = engine.inference_multi_ar(enc, dec, views, ids, tss, [2] + [1] * 8, post_process_function=lambda p: {"raw": p},
+                                             device="cpu", return_mem=True)
+    raw_r = torch.stack([d["raw"] for d in pm])
+    assert rel(digest(raw_r, 65536), g["c2.raw_render"]) < 3e-5
+    assert rel(digest(torch.stack([d["raw"] for d in pm0]), 65536), g["c2.raw_first"]) < 3e-5
+    assert rel(digest(mem[0][11], 16384), g["c2.mem11"]) < 3e-5
+    assert np.array_equal(mem[1][:, ::193].numpy(), g["c2.labels"])

@@ -19,39 +19,41 @@ def _models():
     return tiny_oracle(7)
 
 
-def _views(rank):
+def _views(rank, n=V):
     from must3r_b200 import synthetic as syn
-    return syn.synthetic_views(V, H, W, seed=300 + rank)
+    imgs, ts = syn.synthetic_views(V, H, W, seed=300 + rank)
+    return imgs[:n].contiguous(), ts[:n].contiguous()
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, counts=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from must3r_b200.engine import sharded
     enc, dec = _models()
-    imgs, ts = _views(rank)
-    mem, outs = sharded.inference_sharded(enc, dec, imgs, ts, device="cpu", return_mem=True)
+    imgs, ts = _views(rank, counts[rank] if counts else V)
+    mem, outs = sharded.inference_sharded(enc, dec, imgs, ts, device="cpu", return_mem=True, view_counts=counts)
     q.put((rank, torch.stack(outs).clone(), [m.clone() for m in mem[0]], mem[1].clone()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def _composed_expected(world):
+def _composed_expected(world, counts=None):
     enc, dec = _models()
+    counts = counts or [V] * world
     feats = []
     for r in range(world):
-        imgs, ts = _views(r)
+        imgs, ts = _views(r, counts[r])
         x, pos = enc(imgs, ts)
         feats.append((x, pos, ts))
     x0, p0, t0 = feats[0]
     mem, _ = dec(x0[None, :2], p0[None, :2], t0[None, :2], None)
     mem = list(mem)
-    for s in range(V):
+    for s in range(max(counts)):
         new_parts = []
         for r in range(world):
-            if r == 0 and s < 2:
+            if (r == 0 and s < 2) or s >= counts[r]:
                 continue
             x, pos, ts = feats[r]
             m2, _ = dec(x[None, s:s + 1], pos[None, s:s + 1], ts[None, s:s + 1], tuple(mem))
@@ -90,15 +92,17 @@ def test_world1_equals_reference_chain():
 
 
 @pytest.mark.timeout(300)
-def test_world2_gloo_matches_composed_oracle():
-    world = 2
+@pytest.mark.parametrize("world,counts", [(2, None), (3, [3, 2, 1])])
+def test_gloo_matches_composed_oracle(world, counts):
+    """world 2 with equal shards; world 3 with a ragged split (a fixed scene ceil-split over the ranks: some ranks sit
+    rounds out but still take part in the collective)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     import socket
     with socket.socket() as so:           # a port the kernel says is free right now (fixed numbers collide now and then)
         so.bind(("127.0.0.1", 0))
         port = so.getsockname()[1]
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, counts)) for r in range(world)]
     for p in procs:
         p.start()
     got = {}
@@ -108,7 +112,7 @@ def test_world2_gloo_matches_composed_oracle():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    mem, renders = _composed_expected(world)
+    mem, renders = _composed_expected(world, counts)
     for r in range(world):
         outs, mem_vals, labels = got[r]
         assert torch.equal(labels, mem[1])                                   # identical memory on every rank

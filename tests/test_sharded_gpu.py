@@ -1,5 +1,8 @@
-"""Multi-GPU schedule on real GPUs over NCCL (needs >= 2 devices; skipped otherwise): both exchange paths (fused GEMM ->
-peer stores, NCCL all-gather) must reproduce the schedule composed from single-process decoder calls, bit for bit."""
+"""Multi-GPU schedule on real GPUs (needs >= 2 devices; skipped otherwise): both exchange paths (fused GEMM -> peer stores +
+device-side flag barrier, NCCL all-gather) must reproduce the schedule composed from single-process decoder calls, bit for
+bit (even and ragged view splits, repeated calls on the cached peer arena), and match the schedule composed from the
+unmodified reference at 512x384 (tools/check_sharded.py).  bench.py --gpus N prints the same comparison (`parity`) so the
+driver's scaling run carries it even though its pytest pass sees one GPU."""
 import os
 import subprocess
 import sys
@@ -19,6 +22,6 @@ def test_sharded_schedule_two_gpus(fused):
     port = 29600 + int(fused)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "check_sharded.py")],
-                         env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
-    assert out.stdout.count("memory == composed: True") == 2
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("memory == composed: True") == 6          # 3 cases x 2 ranks
