@@ -587,19 +587,20 @@ def main():
         records["c4_fixed100" if args.config == "c4" else "headline"] = {"ms_per_job": round(ms, 3), "views_per_s": round(value, 2), "n_gpus": world,
                                                                          "job_tflops_per_gpu": round(meta["flops"] / (ms * 1e-3) / 1e12 / world, 1)}
 
-    # ---- CPU baseline on the host cores (rank 0, N=1 only), bounded sample
+    # ---- CPU baseline on the host cores (rank 0, N=1 only), bounded sample.  Run in a fresh interpreter: this process has
+    # imported the reference with the CUDA curope shim for the parity check, and the reference binds its RoPE at import time.
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = effective_cores()
-        ccfg = CONFIGS["c3" if args.config in ("c4", "c5") else args.config]
-        cj, kind = cpu_reference_job(ccfg, args.cpu_views, threads)
-        cj()
-        t0 = time.perf_counter()
-        cj()
-        dtc = time.perf_counter() - t0
-        cpu = {"value": args.cpu_views / dtc, "unit": "views/s", "cores": threads, "kind": kind,
-               "sample": f"first {args.cpu_views} views of {ccfg['label']} (encoder + 2-view init + {args.cpu_views - 2} update(s) + render), fp32, "
-                         f"{'unmodified reference engine (baseline/_ref)' if kind == 'reference' else 'oracle port'}, 1 run after 1 warm-up"}
+        ccfg_id = "c3" if args.config in ("c4", "c5") else args.config
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", ccfg_id, "--steps", "1",
+                                "--warmup", "1", "--cpu-views", str(args.cpu_views)], capture_output=True, text=True, timeout=900,
+                               env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            cpu = json.loads(line)["cpu_baseline"]
+            cpu["sample"] += ", 1 run after 1 warm-up"
+        except Exception as e:  # noqa: BLE001
+            cpu = {"unavailable": f"reference arm failed: {type(e).__name__}: {e}"}
 
     if rank == 0:
         par = "single GPU" if world == 1 else (
