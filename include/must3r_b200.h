@@ -113,6 +113,9 @@ typedef struct {
   int64_t bias_group;
   void* out[M3R_MAX_GROUPS];
   void* peer_out[M3R_MAX_GROUPS * M3R_MAX_PEERS];
+  int32_t max_ctas;           /* > 0: run on at most this many SMs (persistent tile loop).  The memory append runs on a side
+                                 stream next to the last decoder block; its CTAs (slow when they store over NVLink) must not
+                                 take the SMs the LayerNorm-emitting GEMMs of the main chain need to be co-resident */
 } m3r_gemm_group;
 
 int m3r_gemm_grouped(const m3r_gemm_args* args, const m3r_gemm_group* grp, void* stream);

@@ -36,7 +36,7 @@ class GemmArgs(C.Structure):
 
 class GemmGroup(C.Structure):
     _fields_ = [("groups", C.c_int32), ("w_group_rows", C.c_int64), ("bias_group", C.c_int64),
-                ("out", C.c_void_p * 16), ("peer_out", C.c_void_p * (16 * 8))]
+                ("out", C.c_void_p * 16), ("peer_out", C.c_void_p * (16 * 8)), ("max_ctas", C.c_int32)]
 
 
 class AttnArgs(C.Structure):

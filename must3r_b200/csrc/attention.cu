@@ -633,11 +633,20 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     if (splits > key_tiles / 4) splits = key_tiles / 4;        // a split pays ~2 us of partial store + merge: >= 4 tiles each
   } else if (qt == 2 && long_keys) {
     splits = (sms + ctas2 / 2) / ctas2;
+  } else if (qt == 2 && key_tiles >= 64) {
+    //  * throughput shapes whose CTA count is an awkward multiple of the SM count (13 views on one of 8 GPUs: 468 CTAs =
+    //    3.16 waves, 21 % of the last wave's SMs idle): split the long key range 2..4 ways when that fills the waves better
+    //    (every split keeps >= 16 key tiles, so the partial store + merge stays below a few percent)
+    auto eff = [&](int sp) { const long long c = (long long)ctas2 * sp; return (double)c / (double)(((c + sms - 1) / sms) * sms); };
+    double best = eff(1);
+    for (int sp = 2; sp <= 4 && key_tiles / sp >= 16; ++sp)
+      if (eff(sp) > best + 0.04) { best = eff(sp); splits = sp; }
   }
   if (const char* f = getenv("M3R_ATTN_SPLITS")) { const int v = atoi(f); if (v >= 1) splits = v; }
   if (splits > key_tiles) splits = key_tiles;
   if (splits > 32) splits = 32;
   if (splits < 1) splits = 1;
+  if ((long long)a->B * a->H * ((a->Nq + AT_BM - 1) / AT_BM) > 16384 && !getenv("M3R_ATTN_SPLITS")) splits = 1;   // counter table of the split path
   { const int chunk = (key_tiles + splits - 1) / splits; splits = (key_tiles + chunk - 1) / chunk; }   // no empty splits
 
   AttnParams p;
@@ -648,9 +657,9 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   p.part_o = nullptr; p.part_ml = nullptr; p.split_cnt = nullptr;
   p.trace = trace_buffer();
   if (splits > 1) {
-    // scratch layout: [4096 arrival counters | partial O | partial (m, l)].  The counters sit at a fixed place, are
+    // scratch layout: [16384 arrival counters | partial O | partial (m, l)].  The counters sit at a fixed place, are
     // zeroed once when the buffer is (re)allocated and every launch leaves them zero again (last arriver resets).
-    constexpr size_t CNT = 4096;
+    constexpr size_t CNT = 16384;
     const size_t n_cnt = (size_t)a->B * a->H * ((a->Nq + AT_BM - 1) / AT_BM);
     if (n_cnt > CNT) return set_error("attention: too many (batch, head, tile) groups for the split path");
     const size_t need = CNT + (size_t)splits * n_cnt * AT_BM * (HD + 2);     // partial O + (m, l), padded to whole query tiles
