@@ -255,8 +255,8 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
-    if world > 1 and args.config != "c4":
-        raise SystemExit("only C4 (one scene sharded over the GPUs) runs on more than one GPU; C5 does not shard (SURVEY.md 8e)")
+    if world > 1 and args.config not in ("c4", "c5"):
+        raise SystemExit("on more than one GPU: C4 (one scene, views sharded) or C5 (one stream, memory tokens sharded: context parallel)")
 
     import torch.distributed as dist
     from must3r_b200 import _lib, engine, synthetic as syn
@@ -360,6 +360,13 @@ def main():
         """C5: engine.inference_video_multi_ar (keyframe iff id % 3 == 0, window 25), encoder look-ahead in batches of 50."""
         H, W = cfg["H"], cfg["W"]
         enc, dec = get_models(cfg["size"])
+        if world > 1:
+            # one stream on N GPUs: every rank runs the chain on the same frames, the memory TOKENS are sharded and every
+            # cross-attention merges the ranks' partial states through peer memory (engine/context_parallel.py)
+            from must3r_b200.engine.context_parallel import ContextParallelDecoder
+            if "cp" not in models:
+                models["cp"] = ContextParallelDecoder(dec)
+            dec = models["cp"]
         imgs_host, ts = syn.synthetic_views(frames, H, W, seed=3)
         state = {"dev": imgs_host.to(dev)}
         del imgs_host
@@ -532,10 +539,10 @@ def main():
         roof["job_frac_of_peak"] = roof["job_tflops_per_gpu"] / peak
 
     # ---- parity of the timed job (both operand formats) and the other configurations
-    if world > 1:
+    if world > 1 and args.config == "c4":
         parity = sharded_parity(cfg, job, meta)
     elif args.config == "c5":
-        parity = {"unavailable": "stream schedule: parity is covered by the C3 record and tests/test_model_gpu.py::test_stream_*"}
+        parity = {"unavailable": "stream schedule: covered by the C3 / C2 records, tests/test_model_gpu.py::test_stream_schedule_* and tools/check_context_parallel.py"}
     else:
         parity = parity_record(args.config, cfg, job)
     records = {}
@@ -582,8 +589,14 @@ def main():
                 records["c4_fixed100_single_gpu_same_run"] = {"ms_per_job": round(t1, 3), "views_per_s": round(m1["views"] / (t1 / 1e3), 2),
                                                               "note": "reference chain [2]+[1]*98 on rank 0 alone (1 warm-up, 1 timed job)"}
             barrier()
-        if world == 1 and args.config == "c4":
-            pass
+            if args.config == "c4":
+                # the stream configuration on the same GPUs: ONE stream, context-parallel cross-attention
+                fr = args.stream_frames
+                r = rec("c5", lambda: make_stream_job(CONFIGS["c5"], fr), 1, 1, with_parity=False)
+                r["frames"], r["frames_per_s"] = fr, r.pop("views_per_s")
+                r["parallelism"] = f"one stream replicated on {world} GPUs, memory tokens sharded round-robin, per-layer exchange of attention states over NVLink peer memory"
+                r["job_tflops_per_gpu"] = None
+                records["c5_stream_context_parallel"] = r
         records["c4_fixed100" if args.config == "c4" else "headline"] = {"ms_per_job": round(ms, 3), "views_per_s": round(value, 2), "n_gpus": world,
                                                                          "job_tflops_per_gpu": round(meta["flops"] / (ms * 1e-3) / 1e12 / world, 1)}
 
@@ -604,6 +617,8 @@ def main():
 
     if rank == 0:
         par = "single GPU" if world == 1 else (
+            f"ONE stream on {world} GPUs: the chain is replicated, the memory tokens are sharded round-robin and every memory cross-attention "
+            "merges the ranks' attention states exchanged through NVLink peer memory (context parallel)") if args.config == "c5" else (
             f"ONE scene of {meta['views']} views ceil-split over {world} GPUs {meta['counts']}: sharded encoder, rounds of shard-local one-view "
             "updates, new K|V rows stored into every GPU's memory by the GEMM epilogue over NVLink peer memory + one device-side "
             "flag barrier per round, sharded render")

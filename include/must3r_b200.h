@@ -185,9 +185,23 @@ typedef struct {
   int32_t skip_lo, skip_step, skip_len;
   int32_t is_bf16;
   float scale;              /* 1/sqrt(64) */
+  /* Export mode (both non-NULL; O may then be NULL): write the UNNORMALISED attention state of this key set instead of
+   * the normalised output - export_o [B*Nq, H*64] fp32 = sum_j 2^(s_ij*c - m_i) v_j, export_ml [B*Nq, H, 2] fp32 =
+   * (m_i, l_i) with c = scale*log2(e), m_i the running maximum in log2 units (-inf if the row saw no key) - so that key
+   * shards held by different GPUs can be merged exactly (m3r_attn_merge): context-parallel memory cross-attention. */
+  float* export_o;
+  float* export_ml;
 } m3r_attn_args;
 
 int m3r_attention(const m3r_attn_args* args, void* stream);
+
+/* Merge `n` exported attention states of the same queries over disjoint key sets:
+ * out[r, c] = sum_k o_k[r, c] 2^(m_k[r,h] - m) / sum_k l_k[r,h] 2^(m_k[r,h] - m), m = max_k m_k, h = c / 64.
+ * parts_o[k] / parts_ml[k]: device pointers as exported above (rows x H*64 fp32, rows x H x 2 fp32); out: [rows, H*64]
+ * 16-bit with leading dim ldo.  m3r_attn_state_fill writes the state of an EMPTY key set (o = 0, m = -inf, l = 0). */
+int m3r_attn_merge(const float* const* parts_o, const float* const* parts_ml, int32_t n, int64_t rows, int32_t H,
+                   void* out, int64_t ldo, int32_t is_bf16, void* stream);
+int m3r_attn_state_fill(float* export_o, float* export_ml, int64_t rows, int32_t H, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Patch embedding front end: im2col of [V,3,H,W] fp32 images into [V*N, 768] 16-bit rows
@@ -301,7 +315,25 @@ typedef struct {
                                       K|V are projected at use; M3R_MEM_RAW: rows are x (D wide), norm_y + projection at use
                                       (must3r/model/blocks/layers.py:81-96).  All widths "2D" above become D for the last two.
                                       peer output (n_peers > 0) needs M3R_MEM_KV. */
+  /* ---- context-parallel memory cross-attention (no reference counterpart): cp_world > 1 means the
+   * memory tokens of the ONE scene (B == 1, mem_mode kv) are SHARDED over cp_world GPUs, each running this same call on the
+   * same views.  mem[] / Nm describe only THIS rank's rows (Nm may be 0); every rank computes the attention state of the
+   * queries over its shard (m3r_attn_args.export_o), copies it into slot cp_rank of every rank's staging buffer
+   * (m3r_peer_bcast over NVLink), the ranks meet at a device-side flag barrier (m3r_peer_signal / m3r_peer_wait, epoch
+   * cp_epoch0 + layer + 1) and merge the cp_world states (m3r_attn_merge): exactly the softmax over the union of the
+   * shards.  New tokens attend to each other (calls with several views) on rank 0.  Only the rank with cp_owner = 1
+   * appends the call's new rows (mem_out); the others skip the feedback MLP and the append.  The caller guarantees that
+   * the scene's memory is non-empty globally (the very first call of a scene runs without cp). */
+  int32_t cp_world, cp_rank, cp_owner;
+  void* const* cp_stage;           /* host array [cp_world]: rank q's staging buffer as mapped here: 2 * cp_world slots */
+  int64_t cp_slot_bytes;           /* bytes per slot, >= m3r_decoder_cp_slot_bytes() */
+  void* const* cp_flag_slots;      /* host array [cp_world]: this rank's uint32 slot in rank q's flag array */
+  const void* cp_flags_local;      /* this rank's own flag array */
+  uint32_t cp_epoch0;              /* the call consumes epochs cp_epoch0 + 1 .. cp_epoch0 + depth */
 } m3r_decoder_call;
+
+/* bytes of one staging slot for a call with M token rows: M * H * (64 * 4 + 8), rounded up to 256 */
+int64_t m3r_decoder_cp_slot_bytes(const m3r_decoder_weights* w, int64_t M);
 
 int64_t m3r_decoder_workspace_bytes(const m3r_decoder_weights* w, const m3r_decoder_call* call);
 
@@ -320,6 +352,9 @@ int m3r_ipc_close(void* ptr);
  * peer stores must be visible; writes `value` (a monotonically increasing epoch) with system-scope release semantics.
  * m3r_peer_wait(local_flags = this rank's own array, rank_mask, value): a kernel that spins on the GPU until every slot r
  * with bit r of rank_mask set has reached `value`; work enqueued after it sees the rows those ranks stored. */
+/* Copy `bytes` (multiple of 16) from src to the same-sized block dsts[k], k < n: this GPU's staging buffer and its peers'
+ * (NVLink stores): the exchange step of the context-parallel cross-attention. */
+int m3r_peer_bcast(const void* src, void* const* dsts, int32_t n, int64_t bytes, void* stream);
 int m3r_peer_signal(void* const* flag_slots, int32_t n, uint32_t value, void* stream);
 int m3r_peer_wait(const void* local_flags, uint32_t rank_mask, uint32_t value, void* stream);
 

@@ -50,6 +50,7 @@ class AttnArgs(C.Structure):
         ("skip_lo", C.c_int32), ("skip_step", C.c_int32), ("skip_len", C.c_int32),
         ("is_bf16", C.c_int32),
         ("scale", C.c_float),
+        ("export_o", C.c_void_p), ("export_ml", C.c_void_p),
     ]
 
 
@@ -76,6 +77,9 @@ SIGNATURES = {
     "m3r_rope_2d": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64,
                               C.c_int64, C.c_void_p, C.c_float, C.c_float, C.c_void_p]),
     "m3r_attention": (C.c_int, [C.POINTER(AttnArgs), C.c_void_p]),
+    "m3r_attn_merge": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_int64,
+                                 C.c_int32, C.c_void_p]),
+    "m3r_attn_state_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]),
     "m3r_im2col16": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "m3r_unpatchify": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "m3r_postprocess": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -84,6 +88,7 @@ SIGNATURES = {
     "m3r_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "m3r_ipc_open": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "m3r_ipc_close": (C.c_int, [C.c_void_p]),
+    "m3r_peer_bcast": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int64, C.c_void_p]),
     "m3r_peer_signal": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_uint32, C.c_void_p]),
     "m3r_peer_wait": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
 }

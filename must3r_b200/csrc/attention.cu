@@ -62,6 +62,10 @@ struct AttnParams {
   int H;
   long long rows_total;      // B * Nq
   unsigned long long* trace; // debug only (m3r_debug_trace): per-CTA clock stamps, 64 words per CTA; normally null
+  // export mode (context-parallel cross-attention): instead of the normalised 16-bit O, write this launch's UNNORMALISED
+  // (O, m * sl2, l) - after the in-kernel merge of its own key splits - for a later merge with other key shards
+  float* exp_o;              // [B*Nq, H*64] fp32
+  float2* exp_ml;            // [B*Nq, H]
 };
 
 
@@ -447,7 +451,13 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
     float acc[OC];
 #pragma unroll
     for (int d = 0; d < OC; ++d) acc[d] = __uint_as_float(accr[d]);
-    if (q_idx < p.Nq && p.splits == 1) {
+    if (q_idx < p.Nq && p.splits == 1 && p.exp_o != nullptr) {
+      const long long grow = (long long)b * p.Nq + q_idx;
+      float4* e4 = reinterpret_cast<float4*>(p.exp_o + (grow * p.H + h) * HD + half * OC);
+#pragma unroll
+      for (int t = 0; t < OC / 4; ++t) e4[t] = make_float4(acc[4 * t], acc[4 * t + 1], acc[4 * t + 2], acc[4 * t + 3]);
+      if (half == 0) p.exp_ml[grow * p.H + h] = make_float2(m_used == -INFINITY ? -INFINITY : m_used * p.sl2, l_run);
+    } else if (q_idx < p.Nq && p.splits == 1) {
       const long long grow = (long long)b * p.Nq + q_idx;
       const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
       uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD + half * OC);
@@ -528,7 +538,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
             }
           }
           const float inv = l > 0.f ? 1.0f / l : 0.f;      // l is complete after the first pass
-          if (q_idx < p.Nq) {
+          if (q_idx < p.Nq && p.exp_o != nullptr) {
+            float4* e4 = reinterpret_cast<float4*>(p.exp_o + (grow * p.H + h) * HD + half * OC + qd * 16);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) e4[t] = make_float4(a16[4 * t], a16[4 * t + 1], a16[4 * t + 2], a16[4 * t + 3]);
+            if (half == 0 && qd == 0) p.exp_ml[grow * p.H + h] = make_float2(m, l);
+          } else if (q_idx < p.Nq) {
             uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.O) + grow * p.ldo + h * HD + half * OC + qd * 16);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
@@ -584,7 +599,8 @@ static SplitScratch g_split[64];
 // Number of fp32 scratch elements m3r_attention may need for a problem (0 if it will not split).
 extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   using namespace m3r;
-  if (!a || !a->Q || !a->K0 || !a->V0 || !a->O) return set_error("attention: null pointer");
+  if (!a || !a->Q || !a->K0 || !a->V0 || (!a->O && !a->export_o)) return set_error("attention: null pointer");
+  if ((a->export_o == nullptr) != (a->export_ml == nullptr)) return set_error("attention: export_o and export_ml go together");
   if (a->B <= 0 || a->H <= 0 || a->Nq <= 0) return 0;
   if (a->kv_group < 1 || a->B % a->kv_group) return set_error("attention: B (%d) must be a multiple of kv_group (%d)", a->B, a->kv_group);
   if (a->Nk0 < 0 || a->Nk1 < 0 || a->Nk0 + a->Nk1 <= 0) return set_error("attention: no keys");
@@ -655,6 +671,7 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
   p.splits = splits; p.sl2 = a->scale * 1.4426950408889634f;
   p.O = a->O; p.ldo = a->ldo; p.H = a->H; p.rows_total = (long long)a->B * a->Nq;
   p.part_o = nullptr; p.part_ml = nullptr; p.split_cnt = nullptr;
+  p.exp_o = a->export_o; p.exp_ml = reinterpret_cast<float2*>(a->export_ml);
   p.trace = trace_buffer();
   if (splits > 1) {
     // scratch layout: [16384 arrival counters | partial O | partial (m, l)].  The counters sit at a fixed place, are

@@ -230,6 +230,62 @@ __global__ void __launch_bounds__(256) postprocess_kernel(const float* __restric
   }
 }
 
+// ---------------------------------------------------------------------------------------------- attention state merge
+// Context-parallel cross-attention: every GPU exports the unnormalised (O, m, l) of ITS shard of the memory tokens; the
+// states of all shards are merged exactly (same formula as the in-kernel merge of key splits, attention.cu).
+struct PartList { const float* o[M3R_MAX_PEERS]; const float2* ml[M3R_MAX_PEERS]; };
+__global__ void __launch_bounds__(256) attn_merge_kernel(PartList pl, int n, long long rows, int H, uint16_t* __restrict__ out,
+                                                         long long ldo, int is_bf16) {
+  griddep_wait();
+  griddep_launch();
+  const long long total = rows * H * 8;                 // one thread = 8 consecutive output columns of one head
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(i & 7);
+    const long long rh = i >> 3;                        // row * H + h
+    float mk[M3R_MAX_PEERS], lk[M3R_MAX_PEERS];
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < M3R_MAX_PEERS; ++k) if (k < n) { const float2 v = __ldcg(pl.ml[k] + rh); mk[k] = v.x; lk[k] = v.y; m = fmaxf(m, v.x); }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float l = 0.f;
+#pragma unroll
+    for (int k = 0; k < M3R_MAX_PEERS; ++k) if (k < n) {
+      const float w = (mk[k] == -INFINITY) ? 0.f : exp2f(mk[k] - m);
+      l = fmaf(lk[k], w, l);
+      const float4* o4 = reinterpret_cast<const float4*>(pl.o[k] + rh * 64 + c8 * 8);
+      const float4 a = __ldcg(o4), b = __ldcg(o4 + 1);
+      acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+      acc[4] = fmaf(b.x, w, acc[4]); acc[5] = fmaf(b.y, w, acc[5]); acc[6] = fmaf(b.z, w, acc[6]); acc[7] = fmaf(b.w, w, acc[7]);
+    }
+    const float inv = l > 0.f ? 1.0f / l : 0.f;
+    const long long row = rh / H;
+    const int h = int(rh % H);
+    uint4 w4;
+    w4.x = pack16(acc[0] * inv, acc[1] * inv, is_bf16); w4.y = pack16(acc[2] * inv, acc[3] * inv, is_bf16);
+    w4.z = pack16(acc[4] * inv, acc[5] * inv, is_bf16); w4.w = pack16(acc[6] * inv, acc[7] * inv, is_bf16);
+    *reinterpret_cast<uint4*>(out + row * ldo + h * 64 + c8 * 8) = w4;
+  }
+}
+
+__global__ void __launch_bounds__(256) attn_state_fill_kernel(float4* __restrict__ o, long long n_o4, float2* __restrict__ ml, long long n_ml) {
+  griddep_wait();
+  griddep_launch();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_o4; i += (long long)gridDim.x * blockDim.x) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_ml; i += (long long)gridDim.x * blockDim.x) ml[i] = make_float2(-INFINITY, 0.f);
+}
+
+// one source block -> the same offset in n destination buffers (this GPU's and its peers', NVLink stores), 16 B per thread
+struct DstList { uint4* p[M3R_MAX_PEERS]; };
+__global__ void __launch_bounds__(256) peer_bcast_kernel(const uint4* __restrict__ src, DstList dst, int n, long long n_vec) {
+  griddep_wait();
+  griddep_launch();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = src[i];
+#pragma unroll
+    for (int k = 0; k < M3R_MAX_PEERS; ++k) if (k < n) dst.p[k][i] = v;
+  }
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("%s launch: %s", what, cudaGetErrorString(e));
@@ -362,4 +418,34 @@ extern "C" int m3r_postprocess(const float* pm, int64_t P, float* pts3d, float* 
   if (P <= 0) return 0;
   launch_pdl(postprocess_kernel, dim3(grid_for(P, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), pm, (long long)P, pts3d, pts3d_local, conf);
   return check_launch("postprocess");
+}
+
+extern "C" int m3r_attn_merge(const float* const* parts_o, const float* const* parts_ml, int32_t n, int64_t rows, int32_t H,
+                              void* out, int64_t ldo, int32_t is_bf16, void* stream) {
+  if (!parts_o || !parts_ml || !out || n < 1 || n > M3R_MAX_PEERS) return set_error("attn_merge: 1..%d states", M3R_MAX_PEERS);
+  if (rows <= 0) return 0;
+  if (ldo % 8) return set_error("attn_merge: ldo must be a multiple of 8");
+  PartList pl;
+  for (int k = 0; k < M3R_MAX_PEERS; ++k) { pl.o[k] = k < n ? parts_o[k] : nullptr; pl.ml[k] = k < n ? reinterpret_cast<const float2*>(parts_ml[k]) : nullptr; }
+  launch_pdl(attn_merge_kernel, dim3(grid_for(rows * H * 8, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), pl, (int)n,
+             (long long)rows, (int)H, reinterpret_cast<uint16_t*>(out), (long long)ldo, (int)is_bf16);
+  return check_launch("attn_merge");
+}
+
+extern "C" int m3r_attn_state_fill(float* export_o, float* export_ml, int64_t rows, int32_t H, void* stream) {
+  if (!export_o || !export_ml) return set_error("attn_state_fill: null pointer");
+  if (rows <= 0) return 0;
+  launch_pdl(attn_state_fill_kernel, dim3(grid_for(rows * H * 16, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             reinterpret_cast<float4*>(export_o), (long long)(rows * H * 16), reinterpret_cast<float2*>(export_ml), (long long)(rows * H));
+  return check_launch("attn_state_fill");
+}
+
+extern "C" int m3r_peer_bcast(const void* src, void* const* dsts, int32_t n, int64_t bytes, void* stream) {
+  if (!src || !dsts || n < 1 || n > M3R_MAX_PEERS || bytes % 16) return set_error("peer_bcast: 1..%d destinations, bytes %% 16 == 0", M3R_MAX_PEERS);
+  if (bytes <= 0) return 0;
+  DstList dl;
+  for (int k = 0; k < M3R_MAX_PEERS; ++k) dl.p[k] = k < n ? reinterpret_cast<uint4*>(dsts[k]) : nullptr;
+  launch_pdl(peer_bcast_kernel, dim3(grid_for(bytes / 16, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
+             reinterpret_cast<const uint4*>(src), dl, (int)n, (long long)(bytes / 16));
+  return check_launch("peer_bcast");
 }

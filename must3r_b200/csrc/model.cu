@@ -148,6 +148,7 @@ struct DecWs {
   uint16_t *hfb16, *mlpfb16, *hpost16;   // side stream: feedback MLP operands, normalised (new_mem[l] + offset) of every level
   uint16_t *kvmem, *memln;     // memory_mode norm_y / raw: K|V of the stored memory projected at use; LN_y of raw rows
   float *x, *tmp, *snap, *off, *rope, *headout;
+  float *cp_o, *cp_ml;         // context parallel: this rank's exported attention state [M, D] + [M, H, 2], one contiguous block
   int64_t M, Nt;
   int nbm;                     // distinct memory batches behind kvmem (1 when the memory is a stride-0 expand)
   bool merged;                 // one scene, one aspect ratio: K|V of the new tokens live in big16 (no kvnew buffer)
@@ -187,6 +188,11 @@ static int64_t dec_layout(const m3r_decoder_weights* w, const m3r_decoder_call* 
     ws->mlpfb16 = a.take<uint16_t>(M * 4 * D);
     ws->hpost16 = a.take<uint16_t>((int64_t)w->depth * M * D);
   }
+  ws->cp_o = ws->cp_ml = nullptr;
+  if (c->cp_world > 1) {
+    ws->cp_o = a.take<float>(M * D + M * (int64_t)w->num_heads * 2);
+    ws->cp_ml = ws->cp_o + M * D;
+  }
   ws->kvmem = ws->memln = nullptr; ws->nbm = 0;
   if (c->mem_mode != M3R_MEM_KV && c->Nm > 0) {
     ws->nbm = (c->B > 1 && c->mem_bstride_rows == 0) ? 1 : c->B;
@@ -198,6 +204,11 @@ static int64_t dec_layout(const m3r_decoder_weights* w, const m3r_decoder_call* 
 
 }  // namespace m3r
 
+extern "C" int64_t m3r_decoder_cp_slot_bytes(const m3r_decoder_weights* w, int64_t M) {
+  const int64_t b = M * (int64_t)w->embed_dim * 4 + M * (int64_t)w->num_heads * 8;
+  return (b + 255) / 256 * 256;
+}
+
 extern "C" int64_t m3r_decoder_workspace_bytes(const m3r_decoder_weights* w, const m3r_decoder_call* c) {
   DecWs ws;
   return dec_layout(w, c, nullptr, 0, &ws);
@@ -208,13 +219,20 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   if (!w || !c || !workspace || !c->groups) return set_error("decoder_forward: null pointer");
   if (c->B <= 0 || c->G <= 0) return set_error("decoder_forward: empty call");
   if (w->embed_dim != w->num_heads * 64) return set_error("decoder_forward: head_dim must be 64");
-  if (c->render && c->Nm <= 0) return set_error("decoder_forward: render needs a memory (decoder.py:278)");
+  if (c->render && c->Nm <= 0 && c->cp_world <= 1) return set_error("decoder_forward: render needs a memory (decoder.py:278)");
   if (c->Nm > 0 && !c->mem) return set_error("decoder_forward: memory pointers missing");
-  if (!c->render && !c->mem_out) return set_error("decoder_forward: mem_out missing");
+  const bool store_new = !c->render && !(c->cp_world > 1 && !c->cp_owner);     // context parallel: only the owner appends
+  if (store_new && !c->mem_out) return set_error("decoder_forward: mem_out missing");
   if (c->n_peers < 0 || c->n_peers > M3R_MAX_PEERS || (c->n_peers > 0 && (!c->peer_mem || !c->new_only || c->B != 1)))
     return set_error("decoder_forward: peer output needs new_only, one scene and 1..%d peers", M3R_MAX_PEERS);
   if (c->mem_mode < M3R_MEM_KV || c->mem_mode > M3R_MEM_RAW) return set_error("decoder_forward: bad mem_mode %d", c->mem_mode);
   if (c->n_peers > 0 && c->mem_mode != M3R_MEM_KV) return set_error("decoder_forward: peer output needs mem_mode kv");
+  const bool cp = c->cp_world > 1;
+  if (cp) {
+    if (c->cp_world > M3R_MAX_PEERS || c->cp_rank < 0 || c->cp_rank >= c->cp_world) return set_error("decoder_forward: context parallel over 2..%d ranks", M3R_MAX_PEERS);
+    if (c->B != 1 || c->mem_mode != M3R_MEM_KV || c->n_peers > 0 || c->is_init) return set_error("decoder_forward: context parallel needs one scene, mem_mode kv, a continuation call and no peer output");
+    if (!c->cp_stage || !c->cp_flag_slots || !c->cp_flags_local) return set_error("decoder_forward: context-parallel buffers missing");
+  }
   DecWs ws;
   const int64_t need = dec_layout(w, c, workspace, workspace_bytes, &ws);
   if (need > workspace_bytes) return set_error("decoder_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
@@ -230,11 +248,13 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   int n_total = 0;
   for (int g = 0; g < G; ++g) n_total += c->groups[g].n_views;
   // make_mem_mask rule (decoder.py:199-204, 291-296): skip own tokens unless rendering or a lone first image
-  const bool use_skip = !c->render && (Nm > 0 || n_total > 1);
-  SideStream* sd = c->render ? nullptr : side_streams();
+  // (context parallel: the scene's memory is non-empty even when this rank's shard is)
+  const bool use_skip = !c->render && (Nm > 0 || n_total > 1 || cp);
+  if (cp && c->cp_slot_bytes < m3r_decoder_cp_slot_bytes(w, M)) return set_error("decoder_forward: cp_slot_bytes too small");
+  SideStream* sd = store_new ? side_streams() : nullptr;
   if (sd) sd->init();
   const bool side = sd && sd->ok;
-  if (!c->render && Nm > 0 && !c->new_only) {
+  if (store_new && Nm > 0 && !c->new_only) {
     // old memory rows -> output memory tensors (the reference's torch.cat, decoder.py:330) unless the caller appends in
     // place (mem_out[l] == mem[l]); independent of the whole step: copy stream, joined at the end
     cudaStream_t cps = side ? sd->copy : cs;
@@ -371,7 +391,7 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   };
   bool appended = false;
   auto maybe_append = [&](int ready_level) -> int {      // called when X_{ready_level} has been enqueued
-    if (c->render || appended || ready_level != depth - 1) return 0;
+    if (!store_new || appended || ready_level != depth - 1) return 0;
     appended = true;
     if (!side) return 0;                                  // without a side stream the append runs after the head
     M3R_TRY(sd->link(cs, sd->s));
@@ -425,27 +445,52 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     M3R_TRY(res_gemm(ws.att16, D, b.proj_w, D, b.proj_b, xin, xt, nullptr, 1, 0, M, 0));
     // ---- memory cross-attention (layers.py:92-97, attention.py:139-149): q = projq(LN2(x)), K|V = memory (+ new)
     M3R_TRY(gemm(ws.h16, D, b.q_w, D, M, D, D, bf, b.q_b, 0, nullptr, 0, ws.q16, D, M3R_OUT_16, stream));
-    for (int g = 0; g < G; ++g) {
+    // context parallel: does this rank hold any key for this call?  (its memory shard, or - on rank 0 - the other views'
+    // new tokens of a multi-view call)
+    const bool cp_new_keys = cp && !c->render && c->cp_rank == 0 && n_total > 1;
+    const bool cp_has_keys = Nm > 0 || cp_new_keys;
+    if (cp && !cp_has_keys) M3R_TRY(m3r_attn_state_fill(ws.cp_o, ws.cp_ml, M, Hh, stream));
+    for (int g = 0; g < G && (!cp || cp_has_keys); ++g) {
       const m3r_dec_group& gr = c->groups[g];
       m3r_attn_args at = {};
       at.Q = ws.q16 + ws.row0[g] * D; at.ldq = D;
       const uint16_t* mem_l = Nm > 0 ? reinterpret_cast<const uint16_t*>(c->mem[l]) : nullptr;
       const uint16_t* kn = ws.merged ? ws.big16 + 3 * D : ws.kvnew;       // this call's K|V rows
       const int64_t ldn = ws.merged ? 5 * D : 2 * D;
+      if (cp) { at.export_o = ws.cp_o + ws.row0[g] * D; at.export_ml = ws.cp_ml + ws.row0[g] * Hh * 2; }
       if (Nm > 0) {
         if (mode == M3R_MEM_KV) {
           at.K0 = mem_l; at.V0 = mem_l + D; at.ldk0 = 2 * D; at.kv_bstride0 = c->mem_bstride_rows; at.Nk0 = Nm;
         } else {
           at.K0 = ws.kvmem; at.V0 = ws.kvmem + D; at.ldk0 = 2 * D; at.kv_bstride0 = ws.nbm > 1 ? Nm : 0; at.Nk0 = Nm;
         }
-        if (!c->render) { at.K1 = kn; at.V1 = kn + D; at.ldk1 = ldn; at.kv_bstride1 = Nt; at.Nk1 = Nt; }
+        if (!c->render && (!cp || cp_new_keys)) { at.K1 = kn; at.V1 = kn + D; at.ldk1 = ldn; at.kv_bstride1 = Nt; at.Nk1 = Nt; }
       } else {
         at.K0 = kn; at.V0 = kn + D; at.ldk0 = ldn; at.kv_bstride0 = Nt; at.Nk0 = Nt;   // first call: only new tokens
       }
       at.O = ws.att16 + ws.row0[g] * D; at.ldo = D; at.B = B * gr.n_views; at.H = Hh; at.Nq = gr.N;
       at.kv_group = gr.n_views; at.is_bf16 = bf; at.scale = 0.125f;
-      if (use_skip) { at.skip_lo = Nm + (int)ws.tok0[g]; at.skip_step = gr.N; at.skip_len = gr.N; }
+      if (use_skip && at.Nk0 + at.Nk1 > (Nm > 0 ? Nm : 0) ) { at.skip_lo = Nm + (int)ws.tok0[g]; at.skip_step = gr.N; at.skip_len = gr.N; }
       M3R_TRY(m3r_attention(&at, stream));
+    }
+    if (cp) {
+      // exchange: my state -> slot cp_rank of every rank's staging buffer (parity alternates so that a rank one layer ahead
+      // never overwrites what a slower rank still merges), flag barrier, merge of the cp_world states into att16
+      const int par = (int)((c->cp_epoch0 + (uint32_t)l) & 1u);
+      const int64_t bytes = ((int64_t)M * D * 4 + (int64_t)M * Hh * 8 + 15) / 16 * 16;
+      void* dsts[M3R_MAX_PEERS];
+      for (int q = 0; q < c->cp_world; ++q)
+        dsts[q] = reinterpret_cast<uint8_t*>(c->cp_stage[q]) + (int64_t)(par * c->cp_world + c->cp_rank) * c->cp_slot_bytes;
+      M3R_TRY(m3r_peer_bcast(ws.cp_o, dsts, c->cp_world, bytes, stream));
+      const uint32_t epoch = c->cp_epoch0 + (uint32_t)l + 1u;
+      M3R_TRY(m3r_peer_signal(c->cp_flag_slots, c->cp_world, epoch, stream));
+      M3R_TRY(m3r_peer_wait(c->cp_flags_local, (1u << c->cp_world) - 1u, epoch, stream));
+      const float* po[M3R_MAX_PEERS]; const float* pml[M3R_MAX_PEERS];
+      for (int q = 0; q < c->cp_world; ++q) {
+        po[q] = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(c->cp_stage[c->cp_rank]) + (int64_t)(par * c->cp_world + q) * c->cp_slot_bytes);
+        pml[q] = po[q] + (int64_t)M * D;
+      }
+      M3R_TRY(m3r_attn_merge(po, pml, c->cp_world, M, Hh, ws.att16, D, bf, stream));
     }
     M3R_TRY(res_gemm(ws.att16, D, b.cproj_w, D, b.cproj_b, xt, xt, nullptr, 1, 0, M, 0));
     // ---- MLP (layers.py:98)
@@ -462,7 +507,7 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     M3R_TRY(m3r_unpatchify(ws.headout + ws.row0[g] * w->out_dim, B * gr.n_views, gr.H, gr.W, w->out_dim / 256, gr.pointmaps, stream));
   }
 
-  if (!c->render) {
+  if (store_new) {
     if (!side) M3R_TRY(append_memory(stream));
     if (side) {
       M3R_TRY(sd->link(sd->s, cs));                                // join the side stream

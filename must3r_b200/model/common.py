@@ -53,7 +53,10 @@ class DecoderCall(C.Structure):
                 ("mem", C.POINTER(C.c_void_p)), ("mem_bstride_rows", C.c_int64), ("render", C.c_int32),
                 ("is_init", C.c_int32), ("mem_out", C.POINTER(C.c_void_p)), ("mem_out_bstride_rows", C.c_int64),
                 ("new_only", C.c_int32), ("n_peers", C.c_int32), ("peer_mem", C.POINTER(C.c_void_p)),
-                ("mem_mode", C.c_int32)]
+                ("mem_mode", C.c_int32),
+                ("cp_world", C.c_int32), ("cp_rank", C.c_int32), ("cp_owner", C.c_int32),
+                ("cp_stage", C.POINTER(C.c_void_p)), ("cp_slot_bytes", C.c_int64),
+                ("cp_flag_slots", C.POINTER(C.c_void_p)), ("cp_flags_local", C.c_void_p), ("cp_epoch0", C.c_uint32)]
 
 
 MEM_MODE_CODE = {"kv": 0, "norm_y": 1, "raw": 2}        # M3R_MEM_* (must3r/model/blocks/layers.py:9)
@@ -64,6 +67,7 @@ _lib.SIGNATURES.update({
     "m3r_encoder_forward": (C.c_int, [C.POINTER(EncoderWeights), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "m3r_decoder_workspace_bytes": (C.c_int64, [C.POINTER(DecoderWeights), C.POINTER(DecoderCall)]),
+    "m3r_decoder_cp_slot_bytes": (C.c_int64, [C.POINTER(DecoderWeights), C.c_int64]),
     "m3r_decoder_forward": (C.c_int, [C.POINTER(DecoderWeights), C.POINTER(DecoderCall), C.c_void_p, C.c_int64, C.c_void_p]),
 })
 

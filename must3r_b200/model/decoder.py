@@ -250,8 +250,9 @@ class MUSt3R(nn.Module):
 
     @torch.no_grad()
     def forward_list(self, x, pos, true_shape, current_mem=None, render=False, return_feats=False, _new_only=False,
-                     _peer_ptrs=None):
-        """decoder.py:158-265"""
+                     _peer_ptrs=None, _cp=None):
+        """decoder.py:158-265.  `_cp` (engine/context_parallel.py): dict(world, rank, owner, stage_ptrs, slot_bytes, flag_slots,
+        flags_local, epoch0) - the memory is sharded over `world` GPUs and `current_mem` is this rank's shard."""
         if not x[0].is_cuda:
             raise RuntimeError("must3r_b200.MUSt3R runs on CUDA only (no CPU fallback)")
         dev = x[0].device
@@ -321,7 +322,13 @@ class MUSt3R(nn.Module):
             call.mem_bstride_rows = bstrides.pop()
         out_ptrs = (C.c_void_p * self.depth)()
         new_mem = None
-        if not render:
+        if _cp is not None:
+            assert B == 1 and self.memory_mode == "kv" and current_mem is not None and not _new_only and not _peer_ptrs
+            call.cp_world, call.cp_rank, call.cp_owner = _cp["world"], _cp["rank"], 1 if _cp["owner"] else 0
+            call.cp_stage, call.cp_slot_bytes = _cp["stage_ptrs"], _cp["slot_bytes"]
+            call.cp_flag_slots, call.cp_flags_local, call.cp_epoch0 = _cp["flag_slots"], _cp["flags_local"], _cp["epoch0"]
+        store_new = not render and (_cp is None or _cp["owner"])
+        if store_new:
             rows = Nt if _new_only else Nm + Nt
             if _new_only:
                 new_mem = [torch.empty((B, rows, mem_D), dtype=dtype, device=dev) for _ in range(self.depth)]
@@ -357,6 +364,10 @@ class MUSt3R(nn.Module):
             return None, outs, new_mem
         if render:
             out = tuple(current_mem)                                       # decoder.py:251,340: memory returned untouched
+        elif not store_new:
+            # context parallel, another rank stores this call's tokens: this shard is unchanged, the scene's counters advance
+            tot = mem_nimgs + n_total
+            out = (list(mem_vals), labels, tot, tot, labels.shape[1])
         else:
             new_labels, off = [], 0
             for i in range(G):                                             # decoder.py:237-247

@@ -25,3 +25,14 @@ def test_sharded_schedule_two_gpus(fused):
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("memory == composed: True") == 6          # 3 cases x 2 ranks
+
+
+def test_context_parallel_cross_attention_two_gpus():
+    """One stream on 2 GPUs with the memory tokens sharded (engine/context_parallel.py): single calls and the streaming
+    schedule must reproduce the single-GPU chain (tools/check_context_parallel.py)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29621", os.path.join(ROOT, "tools", "check_context_parallel.py")],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
