@@ -6,7 +6,7 @@ with ~360 memory views every one-view step is > 80 % memory cross-attention.  He
 runs the same decoder call on the same frame (the small GEMMs and the self-attention are replicated), computes the
 attention state of the queries over ITS shard of the K|V rows, the states are exchanged through peer memory and merged
 exactly (softmax over the union, like the in-kernel merge of key splits), and only one rank - round-robin over the
-scene's view counter - appends the frame's new rows to its shard.  Results are identical on all ranks and equal to the
+update calls - appends the frame's new rows to its shard.  Results are identical on all ranks and equal to the
 single-GPU chain up to the summation order of the softmax.
 
     dec_cp = ContextParallelDecoder(decoder)              # collective: allocates the peer-mapped staging buffers
@@ -40,6 +40,7 @@ class ContextParallelDecoder:
         self.max_rows = max_rows_per_call
         self.slot_bytes = int(_lib.lib().m3r_decoder_cp_slot_bytes(C.byref(w), max_rows_per_call))
         self.arena = PeerArena(2 * self.world * self.slot_bytes, dev)             # collective
+        self._calls = 0
         self._stage = (C.c_void_p * self.world)(*self.arena.ptrs)
         self._flag_slots = (C.c_void_p * self.world)(*[self.arena.ptrs[r] + self.arena.flag_off + 4 * self.rank for r in range(self.world)])
 
@@ -52,7 +53,9 @@ class ContextParallelDecoder:
         self.dec.reserve_memory(-(-int(n_tokens) // self.world) if n_tokens else 0, growth)
 
     def _cp(self, current_mem, n_views):
-        owner = (int(current_mem[2]) % self.world) == self.rank        # round-robin over the scene's view counter
+        owner = (self._calls % self.world) == self.rank                # round-robin over the update calls (same on every rank)
+        if n_views > 0:
+            self._calls += 1
         cp = dict(world=self.world, rank=self.rank, owner=owner, stage_ptrs=self._stage, slot_bytes=self.slot_bytes,
                   flag_slots=self._flag_slots, flags_local=C.c_void_p(self.arena.ptr + self.arena.flag_off), epoch0=self.arena.epoch)
         self.arena.epoch += self.dec.depth                              # every rank consumes the same epochs
@@ -72,6 +75,17 @@ class ContextParallelDecoder:
                 lab = mem[1][:, :0].contiguous()
                 lab._m3r_labels_host = torch.zeros((0,), dtype=torch.int64)
                 mem = (vals, lab, mem[2], mem[3], 0)
+        elif render and rows > self.max_rows and len(xs) == 1 and xs[0].shape[0] == 1:
+            # a render pass larger than the staging buffers: views are independent given the memory, so go in chunks
+            per_view = int(xs[0].shape[2])
+            step = max(1, self.max_rows // per_view)
+            parts = []
+            for lo in range(0, xs[0].shape[1], step):
+                sl = slice(lo, lo + step)
+                _, pm = self.dec.forward_list([xs[0][:, sl]], [ps[0][:, sl]], [ts[0][:, sl]], current_mem, True,
+                                              _cp=self._cp(current_mem, 0))
+                parts.append(pm[0])
+            mem, pms = tuple(current_mem), [torch.cat(parts, 1)]
         else:
             if rows > self.max_rows:
                 raise RuntimeError(f"context-parallel call with {rows} token rows; the staging buffers hold {self.max_rows} "

@@ -381,6 +381,27 @@ def _update_in_mem(old_values, new_values, old_labels, new_labels, old_idx, new_
     return old_values
 
 
+def _refresh_in_mem(mem_values, mem_labels, old_idx, new_idx):
+    """Keyframe refresh of a refinement pass (engine/inference.py:315-339): the rows labelled old_idx take the values of the
+    rows labelled new_idx, which then disappear.  On one GPU both sets live in the same memory.  With a memory sharded over
+    several GPUs (engine/context_parallel.py) the fresh rows may have been stored by another rank: that rank keeps them
+    under the keyframe's label, and the rank holding the stale rows forgets them - the union of the shards is the same set."""
+    sh = _host_labels(mem_labels)
+    if sh is not None:
+        n_dst, n_src = int((sh == old_idx).sum()), int((sh == new_idx).sum())
+    else:
+        n_dst, n_src = int((mem_labels == old_idx).sum()), int((mem_labels == new_idx).sum())
+    if n_dst == n_src:
+        if n_dst:
+            mem_values = _update_in_mem(mem_values, mem_values, mem_labels, mem_labels, old_idx, new_idx)
+        return _remove_from_mem(mem_values, mem_labels, new_idx)
+    if n_src == 0:
+        return _remove_from_mem(mem_values, mem_labels, old_idx)
+    if n_dst == 0:
+        return mem_values, _restore_label_in_mem(mem_labels, old_idx, new_idx)
+    raise RuntimeError(f"inconsistent memory shards: {n_dst} rows labelled {old_idx}, {n_src} labelled {new_idx}")
+
+
 def _compact_storage(mem):
     """Memory tensors handed back to the caller own exactly their rows (a prefix view would drag the evicted frames'
     storage along, e.g. into a pickle, slam/model.py:431-440)."""
@@ -478,8 +499,9 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
                     if is_kf and seen:             # refinement pass: refresh the stored tokens of this keyframe
                         old = label_of[vid]
                         if old != 0:               # the reference image is never refreshed
-                            mem[0] = _update_in_mem(mem[0], mem[0], mem[1], mem[1], old, new_labels[j])
-                        mem[0], mem[1] = _remove_from_mem(mem[0], mem[1], new_labels[j])
+                            mem[0], mem[1] = _refresh_in_mem(mem[0], mem[1], old, new_labels[j])
+                        else:
+                            mem[0], mem[1] = _remove_from_mem(mem[0], mem[1], new_labels[j])
                     elif seen:                     # known non-keyframe: keep its tokens under the old label
                         mem[1] = _restore_label_in_mem(mem[1], label_of[vid], new_labels[j])
                     else:

@@ -32,7 +32,7 @@ def case(tag, size, H, W, de, dd, F, window):
     enc.load_state_dict(syn.encoder_state_dict(5, depth=de)); dec.load_state_dict(syn.decoder_state_dict(5, depth=dd))
     enc, dec = enc.to(dev).eval(), dec.to(dev).eval()
     N = (H // 16) * (W // 16)
-    cpd = ContextParallelDecoder(dec, max_rows_per_call=3 * N)
+    cpd = ContextParallelDecoder(dec, max_rows_per_call=3 * N)      # the 5-view render below goes in two chunks
     imgs, ts = syn.synthetic_views(F, H, W, seed=77)
     imgs, tsd = imgs.to(dev), ts.to(dev)
     x, pos = enc(imgs, tsd)
