@@ -218,6 +218,11 @@ int m3r_unpatchify(const float* proj, int32_t V, int32_t H, int32_t W, int32_t C
  * pm [P,7] -> pts3d [P,3], pts3d_local [P,3], conf [P]. */
 int m3r_postprocess(const float* pm, int64_t P, float* pts3d, float* pts3d_local, float* conf, void* stream);
 
+/* Nearest-neighbour distance of Q query points [Q,3] fp32 to a database [P,3] fp32: out[i] = min_j |q_i - p_j| (inf for an
+ * empty database).  Replaces the per-frame scipy KD-tree query of the SLAM keyframe test
+ * (must3r/slam/nns.py:57-62, called from must3r/slam/model.py:82). */
+int m3r_nn_min_dist(const float* queries, int32_t Q, const float* db, int64_t P, float* out, void* stream);
+
 /* ===================================================================================================
  * Whole-model entry points: one call enqueues every kernel of a forward pass from C++ (no per-layer
  * Python/ctypes overhead).  Weight structs hold DEVICE pointers (16-bit matrices in nn.Linear layout,

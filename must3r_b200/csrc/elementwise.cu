@@ -286,6 +286,33 @@ __global__ void __launch_bounds__(256) peer_bcast_kernel(const uint4* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------- nearest-neighbour distance
+// out[i] = min_j |q_i - p_j| (inf when the database is empty): the keyframe overlap score of the SLAM front end
+// (must3r/slam/model.py:62-91) queries a scipy KD-tree on the CPU per frame (must3r/slam/nns.py:57-62); here the database
+// points of one viewing-direction quadrant stay on the GPU and are scanned in shared-memory tiles (one query per thread).
+__global__ void __launch_bounds__(256) nn_min_dist_kernel(const float* __restrict__ q, int Q, const float* __restrict__ pdb, long long P,
+                                                          float* __restrict__ out) {
+  __shared__ float sp[1024 * 3];
+  griddep_wait();
+  griddep_launch();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (i < Q) { qx = q[3 * i]; qy = q[3 * i + 1]; qz = q[3 * i + 2]; }
+  float best = INFINITY;
+  for (long long base = 0; base < P; base += 1024) {
+    const int n = (int)((P - base) < 1024 ? (P - base) : 1024);
+    __syncthreads();
+    for (int t = threadIdx.x; t < n * 3; t += blockDim.x) sp[t] = pdb[base * 3 + t];
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const float dx = qx - sp[3 * j], dy = qy - sp[3 * j + 1], dz = qz - sp[3 * j + 2];
+      best = fminf(best, fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+    }
+  }
+  if (i < Q) out[i] = sqrtf(best);
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error("%s launch: %s", what, cudaGetErrorString(e));
@@ -448,4 +475,11 @@ extern "C" int m3r_peer_bcast(const void* src, void* const* dsts, int32_t n, int
   launch_pdl(peer_bcast_kernel, dim3(grid_for(bytes / 16, 256)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream),
              reinterpret_cast<const uint4*>(src), dl, (int)n, (long long)(bytes / 16));
   return check_launch("peer_bcast");
+}
+
+extern "C" int m3r_nn_min_dist(const float* queries, int32_t Q, const float* db, int64_t P, float* out, void* stream) {
+  if (!queries || !out || (P > 0 && !db)) return set_error("nn_min_dist: null pointer");
+  if (Q <= 0) return 0;
+  launch_pdl(nn_min_dist_kernel, dim3((Q + 255) / 256), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), queries, (int)Q, db, (long long)P, out);
+  return check_launch("nn_min_dist");
 }

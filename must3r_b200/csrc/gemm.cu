@@ -59,6 +59,12 @@ struct GemmParams {
   float norm_eps;
   float2* stats;               // [tiles_m][2 * tiles_n][128]
   unsigned int* sync;          // [tiles_m][2]: arrivals, departures (both zero between launches)
+  // split-K of the LayerNorm-emitting kernel (K >= 2048, i.e. fc2): CTA pairs (tile, ks = 0 / 1) each stream half of K;
+  // the ks = 1 CTA hands its fp32 accumulator tile to the ks = 0 CTA through `kpart` and a flag, the ks = 0 CTA adds it and
+  // runs the epilogue.  Halves the bytes ONE SM pulls from L2, which is what bounds these one-wave GEMMs.
+  int ksplit;                  // 1 or 2
+  float4* kpart;               // [tiles][2 column halves][8][128] float4
+  unsigned int* kflag;         // [tiles], zero between launches
 };
 
 // output pointers of a grouped GEMM (passed by value: kernel parameter space)
@@ -194,7 +200,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int tiles_m = tiles_mg * p.groups;
   const int tiles_n = p.N / BN;
   const int num_tiles = tiles_m * tiles_n;
-  const int num_kb = p.K / BK;
+  const int num_kb_all = p.K / BK;
+  // LayerNorm-emitting kernels own exactly one tile per CTA (or per CTA pair with split-K); the others walk tiles persistently
+  const int ksplit = (MODE == MODE_EMIT) ? p.ksplit : 1;
+  const int ks = (MODE == MODE_EMIT) ? (int)blockIdx.x / num_tiles : 0;
+  const int tile0 = (MODE == MODE_EMIT) ? (int)blockIdx.x % num_tiles : (int)blockIdx.x;
+  const int tile_step = (MODE == MODE_EMIT) ? num_tiles : (int)gridDim.x;
+  const int num_kb = num_kb_all / ksplit;
+  const int kb0 = ks * num_kb;
   // tile t -> (group g, m-tile inside the group, n-tile); m-fastest so that co-resident CTAs share the weight tile in L2
   auto a_row0 = [&](int tm) { return (tm / tiles_mg) * p.M + (tm % tiles_mg) * BM; };      // first A row of m-tile tm
   auto w_row0 = [&](int tm, int tn) { return (long long)(tm / tiles_mg) * p.w_group_rows + (long long)tn * BN; };
@@ -223,30 +236,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // BEFORE the programmatic-dependency wait: their (cold, HBM) latency overlaps the predecessor's tail.  The
       // activations follow after the wait; each stage's barrier expects both halves.
       int pre = 0;
-      if (p.w_static && blockIdx.x < num_tiles) {
-        const int n0 = (int)w_row0(blockIdx.x % tiles_m, blockIdx.x / tiles_m);
+      if (p.w_static && tile0 < num_tiles) {
+        const int n0 = (int)w_row0(tile0 % tiles_m, tile0 / tiles_m);
         pre = num_kb < STAGES ? num_kb : STAGES;
         for (int kb = 0; kb < pre; ++kb) {
           mbar_arrive_expect_tx(&full[kb], Cfg::STAGE_BYTES);
-          tma_load_2d(sB + kb * BN * BK * 2, &tmW, &full[kb], kb * BK, n0);
+          tma_load_2d(sB + kb * BN * BK * 2, &tmW, &full[kb], (kb0 + kb) * BK, n0);
         }
       }
       griddep_wait();
       griddep_launch();
       M3R_TR(if (tr) tr[2] = gtime_ns();)
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < num_tiles; t += tile_step) {
         const int m0 = a_row0(t % tiles_m);
         const int n0 = (int)w_row0(t % tiles_m, t / tiles_m);
         for (int kb = 0; kb < num_kb; ++kb) {
           if (pre > 0) {                      // stage already armed, W half in flight
             --pre;
-            tma_load_2d(sA + stage * BM * BK * 2, &tmA, &full[stage], kb * BK, m0);
+            tma_load_2d(sA + stage * BM * BK * 2, &tmA, &full[stage], (kb0 + kb) * BK, m0);
           } else {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-            tma_load_2d(sA + stage * BM * BK * 2, &tmA, &full[stage], kb * BK, m0);
-            tma_load_2d(sB + stage * BN * BK * 2, &tmW, &full[stage], kb * BK, n0);
+            tma_load_2d(sA + stage * BM * BK * 2, &tmA, &full[stage], (kb0 + kb) * BK, m0);
+            tma_load_2d(sB + stage * BN * BK * 2, &tmW, &full[stage], (kb0 + kb) * BK, n0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -263,13 +276,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t idesc = make_idesc(BM, BN, p.is_bf16 ? 1u : 0u, 0, 0);
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = tile0; t < num_tiles; t += tile_step) {
       mbar_wait(&tempty[as], aphase ^ 1);      // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
-        M3R_TR(if (tr && kb == 0 && t == (int)blockIdx.x && (threadIdx.x & 31) == 0) tr[4] = gtime_ns();)
+        M3R_TR(if (tr && kb == 0 && t == tile0 && (threadIdx.x & 31) == 0) tr[4] = gtime_ns();)
         tc_fence_after();
         if (elect_one()) {
           const uint64_t adesc = smem_desc_sw128(smem_u32(sA + stage * BM * BK * 2));
@@ -297,7 +310,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int c_lo = chalf == 0 ? 0 : Cfg::CH0, c_hi = chalf == 0 ? Cfg::CH0 : Cfg::NCHUNK;
     const int lane = threadIdx.x & 31;
     int as = 0; uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = tile0; t < num_tiles; t += tile_step) {
       const int tm = t % tiles_m, tn = t / tiles_m;
       const int g = tm / tiles_mg;
       const int lrow = (tm % tiles_mg) * BM + quarter * 32 + lane;      // row inside the group
@@ -321,6 +334,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tmem_wait_ld();
         tc_fence_before();
         mbar_arrive(&tempty[as]);
+        if (ksplit > 1) {
+          // [tile][column half][8 float4][128 rows]: lanes are consecutive rows -> 512 B per warp request
+          float4* kp = p.kpart + ((long long)(t * 2 + chalf) * 8) * BM + (quarter * 32 + lane);
+          if (ks == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              kp[(long long)i * BM] = make_float4(__uint_as_float(raw[4 * i]), __uint_as_float(raw[4 * i + 1]), __uint_as_float(raw[4 * i + 2]), __uint_as_float(raw[4 * i + 3]));
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (warp == 2 && lane == 0) atom_add_release_u32(p.kflag + t, 1u);
+            continue;                                           // the partner CTA finishes the tile
+          }
+          if (warp == 2 && lane == 0) {
+            unsigned int spins = 0;
+            while (ld_acquire_u32(p.kflag + t) == 0u) { if (++spins > (1u << 26)) __trap(); }
+            p.kflag[t] = 0u;                                    // re-armed for the next launch (nobody else touches it any more)
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 o = __ldcg(kp + (long long)i * BM);
+            raw[4 * i] = __float_as_uint(__uint_as_float(raw[4 * i]) + o.x); raw[4 * i + 1] = __float_as_uint(__uint_as_float(raw[4 * i + 1]) + o.y);
+            raw[4 * i + 2] = __float_as_uint(__uint_as_float(raw[4 * i + 2]) + o.z); raw[4 * i + 3] = __float_as_uint(__uint_as_float(raw[4 * i + 3]) + o.w);
+          }
+        }
         float v[32];
         epilogue_math(p, bias, raw, v, lrow, row_ok, rb_on, rope_row, n0 + c_lo * 32);
         if (!row_ok) {
@@ -428,12 +466,14 @@ static void fill_params(GemmParams& p, const m3r_gemm_args* a) {
   for (int i = 0; i < M3R_MAX_PEERS; ++i) p.peer_out[i] = i < a->n_peer_out ? a->peer_out[i] : nullptr;
   p.groups = 1; p.w_group_rows = 0; p.bias_group = 0;
   p.norm_out = nullptr; p.ldn = 0; p.norm_eps = 0.f; p.stats = nullptr; p.sync = nullptr;
+  p.ksplit = 1; p.kpart = nullptr; p.kflag = nullptr;
 }
 
 // Scratch of the LayerNorm-emitting epilogue, one per device: partial row statistics + arrival / departure counters.
 // Only kernels of ONE stream at a time may use it (they spin on each other's CTAs): the model code emits on the
 // caller's stream only, never on its side streams.
-struct EmitScratch { float2* stats = nullptr; unsigned int* sync = nullptr; };
+struct EmitScratch { float2* stats = nullptr; unsigned int* sync = nullptr; float4* kpart = nullptr; unsigned int* kflag = nullptr; };
+constexpr int EMIT_MAX_KSPLIT_TILES = 80;
 constexpr int EMIT_MAX_TILES_M = 16, EMIT_MAX_PARTS = 24;
 static EmitScratch* emit_scratch() {
   static EmitScratch per_dev[64];
@@ -445,7 +485,13 @@ static EmitScratch* emit_scratch() {
     if (cudaMalloc(&a, sizeof(float2) * EMIT_MAX_TILES_M * EMIT_MAX_PARTS * BM) != cudaSuccess) return nullptr;
     if (cudaMalloc(&b, sizeof(unsigned int) * 2 * EMIT_MAX_TILES_M) != cudaSuccess) { cudaFree(a); return nullptr; }
     if (cudaMemset(b, 0, sizeof(unsigned int) * 2 * EMIT_MAX_TILES_M) != cudaSuccess) { cudaFree(a); cudaFree(b); return nullptr; }
+    void* c = nullptr; void* d = nullptr;
+    if (cudaMalloc(&c, sizeof(float) * EMIT_MAX_KSPLIT_TILES * BM * 64) != cudaSuccess) { cudaFree(a); cudaFree(b); return nullptr; }
+    if (cudaMalloc(&d, sizeof(unsigned int) * EMIT_MAX_KSPLIT_TILES) != cudaSuccess || cudaMemset(d, 0, sizeof(unsigned int) * EMIT_MAX_KSPLIT_TILES) != cudaSuccess) {
+      cudaFree(a); cudaFree(b); cudaFree(c); return nullptr;
+    }
     e.stats = reinterpret_cast<float2*>(a); e.sync = reinterpret_cast<unsigned int*>(b);
+    e.kpart = reinterpret_cast<float4*>(c); e.kflag = reinterpret_cast<unsigned int*>(d);
   }
   return &e;
 }
@@ -472,6 +518,11 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream, const m3r_ge
     EmitScratch* e = emit_scratch();
     if (!e) return set_error("gemm: LayerNorm-emit scratch allocation failed");
     p.norm_out = a->norm_out; p.ldn = a->ldn; p.norm_eps = a->norm_eps; p.stats = e->stats; p.sync = e->sync;
+    static int ks_env = -1;
+    if (ks_env < 0) { const char* v = getenv("M3R_KSPLIT"); ks_env = (v && v[0] == '0') ? 0 : 1; }
+    if (ks_env && a->K >= 2048 && (a->K / BK) % 2 == 0 && 2 * tiles <= num_sms() && tiles <= EMIT_MAX_KSPLIT_TILES) {
+      p.ksplit = 2; p.kpart = e->kpart; p.kflag = e->kflag;
+    }
   }
   static bool attr_set[64] = {};
   int dev = 0; cudaGetDevice(&dev);
@@ -481,8 +532,9 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream, const m3r_ge
     attr_set[dev] = true;
   }
   int grid = tiles < num_sms() ? tiles : num_sms();
+  if (MODE == MODE_EMIT) grid = tiles * p.ksplit;
   if (MODE == MODE_GROUPED && grp->max_ctas > 0 && grid > grp->max_ctas) grid = grp->max_ctas;
-  if (MODE == MODE_EMIT && tiles > grid) return set_error("gemm: LayerNorm-emitting epilogue needs one tile per CTA (%d tiles, %d SMs)", tiles, grid);
+  if (MODE == MODE_EMIT && grid > num_sms()) return set_error("gemm: LayerNorm-emitting epilogue needs one tile per CTA (%d tiles, %d SMs)", tiles, grid);
   {
     const int cat = BN >= 256 ? PROF_GEMM256 : (BN >= 128 ? PROF_GEMM128 : PROF_GEMM64);
     ProfScope prof(cat, 2.0 * a->M * groups * (double)a->N * a->K, 2.0 * ((double)a->M * groups * a->K + (double)a->N * groups * a->K) + (double)a->M * groups * a->N * (a->out_dtype ? 2 : 4), stream);

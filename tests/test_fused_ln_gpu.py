@@ -22,7 +22,8 @@ def rnd(*shape, dtype=torch.float32, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("M,N,K", [(768, 768, 768), (1536, 768, 3072), (196, 768, 768), (100, 128, 64), (392, 768, 1024), (1372, 768, 768)])
+@pytest.mark.parametrize("M,N,K", [(768, 768, 768), (1536, 768, 3072), (196, 768, 768), (100, 128, 64), (392, 768, 1024), (1372, 768, 768),
+                                   (768, 768, 3072), (196, 768, 3072), (900, 512, 2048)])   # the last three: split-K CTA pairs
 def test_gemm_emits_layernorm(dtype, M, N, K):
     """x = res + a W^T + b (fp32) and norm_out = (x - mean) / sqrt(var + eps) in one launch; rows with a large common
     offset check that the cross-tile (mean, M2) combination is as good as a two-pass LayerNorm."""
