@@ -25,6 +25,8 @@ struct GemmCfg {
   static constexpr int NCHUNK = BN / 32;                     // 32-column epilogue chunks
   static constexpr int CH0 = (NCHUNK + 1) / 2;               // chunks drained by the first warp of a lane quarter; the second takes the rest
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int PEER_STAGE_BYTES = 8 * 4096;          // per epilogue warp 32 rows x 128 B: transposes peer stores (below)
+  static constexpr int SMEM_BYTES_PEER = SMEM_BYTES + PEER_STAGE_BYTES;
 };
 
 struct GemmParams {
@@ -425,6 +427,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tc_fence_before();
           mbar_arrive(&tempty[as]);
         }
+        if (p.n_peer_out > 0 && p.out_dtype != 0) {
+          // ---- fused GEMM -> all-gather epilogue.  A thread owns one ROW of the tile, so direct peer stores would be 32
+          // scattered 16-byte pieces per instruction - partial sectors over NVLink (measured 180 GB/s at 8 GPUs, r02_run6).
+          // The warp's rows x (up to) 64 columns go through a swizzled shared-memory tile and leave as 128-byte row segments:
+          // one store instruction = 4 rows x 128 B (8 lanes per row), full sectors, to every peer's buffer.
+          uint4* stg = reinterpret_cast<uint4*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 256;      // [32 rows][8 x 16 B]
+          const int row_base = (tm % tiles_mg) * BM + quarter * 32;
+#pragma unroll 1
+          for (int c = c_lo; c < c_hi; c += 2) {
+            const int nch = (c_hi - c) < 2 ? (c_hi - c) : 2;
+            for (int u = 0; u < nch; ++u) {
+              uint32_t raw[32];
+              tmem_ld32(t_addr + (c + u) * 32, raw);
+              tmem_wait_ld();
+              if (c + u == c_hi - 1) { tc_fence_before(); mbar_arrive(&tempty[as]); }
+              float v[32];
+              epilogue_math(p, bias, raw, v, lrow, row_ok, rb_on, rope_row, n0 + (c + u) * 32);
+              uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out_g) + orow * p.ldc + n0 + (c + u) * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 w;
+                w.x = pack16(v[8 * i], v[8 * i + 1], p.is_bf16); w.y = pack16(v[8 * i + 2], v[8 * i + 3], p.is_bf16);
+                w.z = pack16(v[8 * i + 4], v[8 * i + 5], p.is_bf16); w.w = pack16(v[8 * i + 6], v[8 * i + 7], p.is_bf16);
+                if (row_ok) o4[i] = w;                                  // this GPU's copy: the thread's own row
+                stg[lane * 8 + ((u * 4 + i) ^ (lane & 7))] = w;
+              }
+            }
+            __syncwarp();
+            const int lpr = 4 * nch, rpi = 32 / lpr;                    // lanes per row, rows per store instruction
+            for (int k = 0; k < lpr; ++k) {
+              const int r = k * rpi + lane / lpr, piece = lane % lpr;
+              const int row_r = row_base + r;
+              if (row_r < p.M) {
+                long long orow_r = row_r;
+                if (p.rows_per_batch > 0) orow_r = (long long)(row_r / p.rows_per_batch) * p.batch_stride_rows + row_r % p.rows_per_batch;
+                const uint4 val = stg[r * 8 + (piece ^ (r & 7))];
+                for (int pr = 0; pr < p.n_peer_out; ++pr)
+                  reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(peers_g[pr]) + orow_r * p.ldc + n0 + c * 32)[piece] = val;
+              }
+            }
+            __syncwarp();
+          }
+        } else
 #pragma unroll 1
         for (int c = c_lo; c < c_hi; ++c) {
           uint32_t raw[32];
@@ -527,7 +572,7 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream, const m3r_ge
   static bool attr_set[64] = {};
   int dev = 0; cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES_PEER);
     if (e != cudaSuccess) return set_error("gemm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[dev] = true;
   }
@@ -538,7 +583,8 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream, const m3r_ge
   {
     const int cat = BN >= 256 ? PROF_GEMM256 : (BN >= 128 ? PROF_GEMM128 : PROF_GEMM64);
     ProfScope prof(cat, 2.0 * a->M * groups * (double)a->N * a->K, 2.0 * ((double)a->M * groups * a->K + (double)a->N * groups * a->K) + (double)a->M * groups * a->N * (a->out_dtype ? 2 : 4), stream);
-    cudaError_t le = launch_pdl(gemm_kernel<BN, MODE>, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmW, p, tab);
+    const size_t smem_bytes = (a->n_peer_out > 0 && a->out_dtype != 0) ? Cfg::SMEM_BYTES_PEER : Cfg::SMEM_BYTES;
+    cudaError_t le = launch_pdl(gemm_kernel<BN, MODE>, dim3(grid), dim3(GEMM_THREADS), smem_bytes, stream, tmA, tmW, p, tab);
     if (le != cudaSuccess) return set_error("gemm launch: %s", cudaGetErrorString(le));
   }
   cudaError_t e = cudaGetLastError();

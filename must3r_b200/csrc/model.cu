@@ -368,7 +368,9 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
         m3r_gemm_group grp = {};
         grp.groups = depth; grp.w_group_rows = 5 * D; grp.bias_group = 5 * D;
         // next to the main chain (side stream): leave the SMs a LayerNorm-emitting GEMM needs (one wave of 128x64 tiles)
-        if (st != stream) { const int keep = tiles_m * (D / 64); const int left = num_sms() - keep; grp.max_ctas = left > 32 ? left : 32; }
+        static int cap_env = -1;
+        if (cap_env < 0) { const char* e = getenv("M3R_APPEND_CAP"); cap_env = (e && e[0] == '0') ? 0 : 1; }
+        if (st != stream && cap_env) { const int keep = tiles_m * (D / 64); const int left = num_sms() - keep; grp.max_ctas = left > 32 ? left : 32; }
         a.A = ws.hpost16; a.W = reinterpret_cast<const uint16_t*>(w->blocks[0].a_w) + (int64_t)3 * D * D; a.bias = w->blocks[0].a_b + 3 * D;
         for (int l = 0; l < depth; ++l) {
           grp.out[l] = reinterpret_cast<uint16_t*>(c->mem_out[l]) + orow * 2 * D;

@@ -17,7 +17,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_loader.available(), re
 
 
 def _ref():
-    ref_loader.load_reference(curope_shim="curope" in sys.modules)
+    ref_loader.load_reference(curope_shim=True)       # one RoPE choice per process: every GPU test loads the reference with the shim
     return importlib.import_module("must3r.slam.nns"), importlib.import_module("must3r.slam.model")
 
 
