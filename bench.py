@@ -525,8 +525,14 @@ def main():
         tensor_cats = [c for c in cats if prof[c]["flops"] > 0]
         dom = max(tensor_cats, key=lambda c: prof[c]["ms"])
         ach = prof[dom]["flops"] / (prof[dom]["ms"] * 1e-3) / 1e12 if prof[dom]["ms"] > 0 else 0.0
+        # dram__bytes_read + dram__bytes_write of ONE representative launch of the dominant category, taken from the committed
+        # `ncu --set full` captures (bench.py cannot run ncu itself); the file names the launch shape and the summary it came from
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json"))).get(dom, {})
+        except Exception:  # noqa: BLE001
+            traffic = {}
         roof = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "traffic_note": "dram bytes of single launches are in the committed ncu summaries (profiles/r02_ncu_*): a category mixes several shapes, so no single constant is quoted here",
+                "traffic": traffic.get("dram_bytes"), "traffic_of": traffic.get("launch"), "traffic_source": traffic.get("source"),
                 "peak_source": peak_src,
                 "note": "per-launch CUDA events serialise the side streams: the category times sum to more than the step; shares are indicative",
                 "per_kernel": {c: {"ms": round(p["ms"], 3), "launches": p["launches"],

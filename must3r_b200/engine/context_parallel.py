@@ -29,37 +29,23 @@ from ..model import common as cm
 from .peer import PeerArena
 
 
-class ContextParallelDecoder:
-    def __init__(self, decoder, max_rows_per_call: int = 2 * 768):
-        assert dist.is_initialized() and decoder.memory_mode == "kv"
-        self.dec = decoder
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        assert self.world <= 8
-        dev = decoder.norm_dec.weight.device
-        w = decoder._packed(cm.get_precision())
-        self.max_rows = max_rows_per_call
-        self.slot_bytes = int(_lib.lib().m3r_decoder_cp_slot_bytes(C.byref(w), max_rows_per_call))
-        self.arena = PeerArena(2 * self.world * self.slot_bytes, dev)             # collective
+class ShardedMemoryDecoder:
+    """Sharding policy shared by the CUDA wrapper below and by the CPU emulation the tests drive the engine with
+    (tests/test_context_parallel_cpu.py): which rank stores a call's new tokens, what an empty shard looks like, how a
+    large render is chunked.  Subclasses implement `_first(xs, ps, ts)` (the scene's first call, replicated) and
+    `_run(xs, ps, ts, current_mem, render, owner)` (a call on the sharded memory)."""
+
+    rank, world = 0, 1
+    max_rows = 1 << 62
+
+    def __init__(self):
         self._calls = 0
-        self._stage = (C.c_void_p * self.world)(*self.arena.ptrs)
-        self._flag_slots = (C.c_void_p * self.world)(*[self.arena.ptrs[r] + self.arena.flag_off + 4 * self.rank for r in range(self.world)])
 
-    # attributes the engine / callers read
-    def __getattr__(self, name):
-        return getattr(self.dec, name)
-
-    def reserve_memory(self, n_tokens: int = 0, growth: float = 0.0):
-        # a shard receives ~1/world of the scene's tokens
-        self.dec.reserve_memory(-(-int(n_tokens) // self.world) if n_tokens else 0, growth)
-
-    def _cp(self, current_mem, n_views):
+    def _next_owner(self, stores: bool) -> bool:
         owner = (self._calls % self.world) == self.rank                # round-robin over the update calls (same on every rank)
-        if n_views > 0:
+        if stores:
             self._calls += 1
-        cp = dict(world=self.world, rank=self.rank, owner=owner, stage_ptrs=self._stage, slot_bytes=self.slot_bytes,
-                  flag_slots=self._flag_slots, flags_local=C.c_void_p(self.arena.ptr + self.arena.flag_off), epoch0=self.arena.epoch)
-        self.arena.epoch += self.dec.depth                              # every rank consumes the same epochs
-        return cp
+        return owner
 
     @torch.no_grad()
     def __call__(self, x, pos, true_shape, current_mem=None, render=False, return_feats=False):
@@ -69,7 +55,7 @@ class ContextParallelDecoder:
         rows = sum(int(v.shape[0] * v.shape[1] * v.shape[2]) for v in xs)
         if current_mem is None:
             # first call of the scene: no memory yet, replicated on every rank; rank 0 keeps the tokens
-            mem, pms = self.dec.forward_list(xs, ps, ts, None, render)
+            mem, pms = self._first(xs, ps, ts)
             if self.rank != 0:
                 vals = [v[:, :0] for v in mem[0]]
                 lab = mem[1][:, :0].contiguous()
@@ -82,19 +68,50 @@ class ContextParallelDecoder:
             parts = []
             for lo in range(0, xs[0].shape[1], step):
                 sl = slice(lo, lo + step)
-                _, pm = self.dec.forward_list([xs[0][:, sl]], [ps[0][:, sl]], [ts[0][:, sl]], current_mem, True,
-                                              _cp=self._cp(current_mem, 0))
+                _, pm = self._run([xs[0][:, sl]], [ps[0][:, sl]], [ts[0][:, sl]], current_mem, True, False)
                 parts.append(pm[0])
             mem, pms = tuple(current_mem), [torch.cat(parts, 1)]
         else:
             if rows > self.max_rows:
                 raise RuntimeError(f"context-parallel call with {rows} token rows; the staging buffers hold {self.max_rows} "
                                    "(ContextParallelDecoder(max_rows_per_call=...))")
-            n_views = sum(int(v.shape[1]) for v in xs)
-            mem, pms = self.dec.forward_list(xs, ps, ts, current_mem, render, _cp=self._cp(current_mem, n_views))
+            mem, pms = self._run(xs, ps, ts, current_mem, render, self._next_owner(not render))
         return (mem, pms) if as_list else (mem, pms[0])
 
     forward = __call__
+
+
+class ContextParallelDecoder(ShardedMemoryDecoder):
+    def __init__(self, decoder, max_rows_per_call: int = 2 * 768):
+        super().__init__()
+        assert dist.is_initialized() and decoder.memory_mode == "kv"
+        self.dec = decoder
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        assert self.world <= 8
+        dev = decoder.norm_dec.weight.device
+        w = decoder._packed(cm.get_precision())
+        self.max_rows = max_rows_per_call
+        self.slot_bytes = int(_lib.lib().m3r_decoder_cp_slot_bytes(C.byref(w), max_rows_per_call))
+        self.arena = PeerArena(2 * self.world * self.slot_bytes, dev)             # collective
+        self._stage = (C.c_void_p * self.world)(*self.arena.ptrs)
+        self._flag_slots = (C.c_void_p * self.world)(*[self.arena.ptrs[r] + self.arena.flag_off + 4 * self.rank for r in range(self.world)])
+
+    # attributes the engine / callers read
+    def __getattr__(self, name):
+        return getattr(self.dec, name)
+
+    def reserve_memory(self, n_tokens: int = 0, growth: float = 0.0):
+        # a shard receives ~1/world of the scene's tokens
+        self.dec.reserve_memory(-(-int(n_tokens) // self.world) if n_tokens else 0, growth)
+
+    def _first(self, xs, ps, ts):
+        return self.dec.forward_list(xs, ps, ts, None, False)
+
+    def _run(self, xs, ps, ts, current_mem, render, owner):
+        cp = dict(world=self.world, rank=self.rank, owner=owner, stage_ptrs=self._stage, slot_bytes=self.slot_bytes,
+                  flag_slots=self._flag_slots, flags_local=C.c_void_p(self.arena.ptr + self.arena.flag_off), epoch0=self.arena.epoch)
+        self.arena.epoch += self.dec.depth                              # every rank consumes the same epochs
+        return self.dec.forward_list(xs, ps, ts, current_mem, render, _cp=cp)
 
     def gather_memory(self, mem):
         """Debug / test helper: the scene's whole memory (rows of all shards, sorted by label) on every rank."""

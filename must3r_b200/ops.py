@@ -193,12 +193,17 @@ def rope_2d(tokens: torch.Tensor, positions: torch.Tensor, base: float, fwd: flo
 def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, *, B: int, H: int, Nq: int, Nk0: int,
               kv_bstride0: Optional[int] = None, k1: Optional[torch.Tensor] = None, v1: Optional[torch.Tensor] = None,
               Nk1: int = 0, kv_bstride1: Optional[int] = None, kv_group: int = 1, skip_lo: int = 0, skip_step: int = 0,
-              skip_len: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q: 2-D view [B*Nq, >=H*64] (row stride arbitrary); k/v: 2-D views whose rows are keys.  Returns [B*Nq, H*64]."""
+              skip_len: int = 0, out: Optional[torch.Tensor] = None, export: bool = False):
+    """q: 2-D view [B*Nq, >=H*64] (row stride arbitrary); k/v: 2-D views whose rows are keys.  Returns [B*Nq, H*64], or with
+    export=True the unnormalised attention state (o [B*Nq, H*64] fp32, ml [B*Nq, H, 2] fp32) of this key set (attn_merge)."""
     _req_cuda(q, k0, v0)
     assert q.dtype in F16 and q.stride(-1) == 1 and k0.stride(-1) == 1 and v0.stride(-1) == 1
     assert k0.stride(0) == v0.stride(0)
-    if out is None:
+    exp_o = exp_ml = None
+    if export:
+        exp_o = torch.empty((B * Nq, H * 64), device=q.device, dtype=torch.float32)
+        exp_ml = torch.empty((B * Nq, H, 2), device=q.device, dtype=torch.float32)
+    elif out is None:
         out = torch.empty((B * Nq, H * 64), device=q.device, dtype=q.dtype)
     a = _lib.AttnArgs()
     a.Q, a.ldq = q.data_ptr(), q.stride(0)
@@ -208,13 +213,36 @@ def attention(q: torch.Tensor, k0: torch.Tensor, v0: torch.Tensor, *, B: int, H:
         assert k1.stride(0) == v1.stride(0)
         a.K1, a.V1, a.ldk1, a.Nk1 = k1.data_ptr(), v1.data_ptr(), k1.stride(0), Nk1
         a.kv_bstride1 = Nk1 if kv_bstride1 is None else kv_bstride1
-    a.O, a.ldo = out.data_ptr(), out.stride(0)
+    if export:
+        a.export_o, a.export_ml, a.ldo = exp_o.data_ptr(), exp_ml.data_ptr(), H * 64
+    else:
+        a.O, a.ldo = out.data_ptr(), out.stride(0)
     a.B, a.H, a.Nq, a.kv_group = B, H, Nq, kv_group
     a.skip_lo, a.skip_step, a.skip_len = skip_lo, skip_step, skip_len
     a.is_bf16 = F16[q.dtype]
     a.scale = 0.125
     _lib.check(_lib.lib().m3r_attention(C.byref(a), _stream()), "attention")
+    return (exp_o, exp_ml) if export else out
+
+
+def attn_merge(states, dtype: torch.dtype) -> torch.Tensor:
+    """Merge attention states [(o, ml), ...] of the same queries over disjoint key sets -> normalised [rows, H*64] 16-bit."""
+    n = len(states)
+    rows, HD = states[0][0].shape
+    H = HD // 64
+    out = torch.empty((rows, HD), device=states[0][0].device, dtype=dtype)
+    po = (C.c_void_p * n)(*[o.data_ptr() for o, _ in states])
+    pml = (C.c_void_p * n)(*[ml.data_ptr() for _, ml in states])
+    _lib.check(_lib.lib().m3r_attn_merge(po, pml, n, rows, H, _p(out), out.stride(0), F16[dtype], _stream()), "attn_merge")
     return out
+
+
+def attn_state_fill(rows: int, H: int, device) -> tuple:
+    """The attention state of an empty key set: o = 0, m = -inf, l = 0."""
+    o = torch.empty((rows, H * 64), device=device, dtype=torch.float32)
+    ml = torch.empty((rows, H, 2), device=device, dtype=torch.float32)
+    _lib.check(_lib.lib().m3r_attn_state_fill(_p(o), _p(ml), rows, H, _stream()), "attn_state_fill")
+    return o, ml
 
 
 def im2col16(img: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:

@@ -1,6 +1,8 @@
 """Host logic of must3r_b200.engine (view grouping, update/refine/evict bookkeeping, chunked render) pinned
 against the reference engine's outputs (tests/golden/engine.npz), with the CPU oracle standing in as the model.
 fp32 vs fp32: 3e-5 rel-L2."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -209,3 +211,29 @@ def test_postprocess_cpu_matches_oracle():
     ref = orc.postprocess(pm)
     for k in ref:
         assert torch.allclose(out[k], ref[k])
+
+
+def test_memory_pickle_roundtrip_in_reference_layout(tmp_path):
+    """engine.save_memory / load_memory write the (memory, keyframe_pointmaps, overlap_tree) pickle of
+    must3r/slam/model.py:431-440; a memory made of views into larger buffers (evicted stream, growable arena) is stored
+    compactly and can be resumed: continuing the stream from the loaded memory gives the results of the uninterrupted run."""
+    import pickle as pkl
+    from must3r_b200 import engine
+    enc, dec = tiny_oracle(7)
+    imgs, ts = syn.synthetic_views(8, 32, 48, seed=51)
+    views, tss = list(imgs.unbind(0)), list(ts.unbind(0))
+    kw = dict(post_process_function=lambda p: {"raw": p}, device="cpu", return_mem=True, local_context_size=3)
+    mem_all, out_all = engine.inference_video_multi_ar(enc, dec, views, tss, [2] + [1] * 6, **kw)
+    mem5, _ = engine.inference_video_multi_ar(enc, dec, views[:5], tss[:5], [2] + [1] * 3, **kw)
+    path = os.path.join(tmp_path, "mem.pkl")
+    engine.save_memory(path, mem5, keyframe_pointmaps={"n": 5})
+    raw = pkl.load(open(path, "rb"))
+    assert isinstance(raw, tuple) and len(raw) == 3 and raw[1] == {"n": 5} and raw[2] is None
+    for v in raw[0][0]:
+        assert v.is_contiguous() and v.untyped_storage().nbytes() == v.numel() * v.element_size() and not hasattr(v, "_m3r_arena")
+    mem, data, tree = engine.load_memory(path)
+    assert torch.equal(mem[1], mem5[1]) and all(torch.equal(a, b) for a, b in zip(mem[0], mem5[0])) and list(mem[2:]) == [int(v) for v in mem5[2:]]
+    x, pos = enc(imgs[5:6], ts[5:6])
+    m_a, p_a = dec(x[None], pos[None], ts[None, 5:6], tuple(mem))
+    m_b, p_b = dec(x[None], pos[None], ts[None, 5:6], tuple(mem5))
+    assert torch.equal(p_a, p_b)

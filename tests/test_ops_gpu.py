@@ -333,3 +333,46 @@ def test_errors_are_loud():
         ops.linear(a, torch.zeros(64, 96, device="cuda", dtype=torch.float16))
     with pytest.raises(RuntimeError):
         ops.linear(a.cpu(), a.cpu())
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("B,H,Nq,Nk,shards", [(1, 12, 768, 7680, 4), (2, 3, 200, 1000, 3), (1, 12, 768, 76800, 8), (1, 2, 130, 300, 2)])
+def test_attention_state_export_and_merge(dtype, B, H, Nq, Nk, shards):
+    """Context-parallel building blocks on one GPU: the key range cut into `shards` pieces (uneven, one of them empty),
+    every piece exported as an unnormalised attention state (with and without in-kernel key splits), the states merged
+    (m3r_attn_merge) == attention over all keys."""
+    D = H * 64
+    q = rnd(B * Nq, D, dtype=dtype, seed=1)
+    kv = rnd(B * Nk, 2 * D, dtype=dtype, seed=2)
+    ref = ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk).float()
+    cuts = sorted({0, Nk} | {int(Nk * f) for f in torch.linspace(0.13, 0.9, shards - 1).tolist()})
+    states = []
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+        kvs = kv.view(B, Nk, 2 * D)[:, lo:hi].contiguous().view(B * (hi - lo), 2 * D)
+        states.append(ops.attention(q, kvs[:, :D], kvs[:, D:], B=B, H=H, Nq=Nq, Nk0=hi - lo, export=True))
+    states.insert(1, ops.attn_state_fill(B * Nq, H, q.device))             # a rank whose shard is empty
+    got = ops.attn_merge(states, dtype).float()
+    assert rel_l2(got, ref) < (6e-4 if dtype == torch.float16 else 5e-3)
+    # a single state merges to plain attention
+    one = ops.attn_merge([ops.attention(q, kv[:, :D], kv[:, D:], B=B, H=H, Nq=Nq, Nk0=Nk, export=True)], dtype).float()
+    assert rel_l2(one, ref) < (3e-4 if dtype == torch.float16 else 3e-3)
+
+
+def test_peer_primitives_on_one_gpu():
+    """m3r_peer_bcast / m3r_peer_signal / m3r_peer_wait with this GPU as its own only peer: data lands in every destination, the
+    wait returns once the epoch is published (stream order), and a wait for an epoch that was already passed returns at once."""
+    import ctypes as C
+    from must3r_b200 import _lib
+    lib = _lib.lib()
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    src = torch.randn(1 << 16, device="cuda")
+    dsts = [torch.zeros_like(src) for _ in range(3)]
+    arr = (C.c_void_p * 3)(*[d.data_ptr() for d in dsts])
+    _lib.check(lib.m3r_peer_bcast(C.c_void_p(src.data_ptr()), arr, 3, src.numel() * 4, sp), "peer_bcast")
+    flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+    slots = (C.c_void_p * 1)(flags.data_ptr() + 4 * 2)                     # "rank 2" publishes
+    _lib.check(lib.m3r_peer_signal(slots, 1, 7, sp), "peer_signal")
+    _lib.check(lib.m3r_peer_wait(C.c_void_p(flags.data_ptr()), 1 << 2, 7, sp), "peer_wait")
+    _lib.check(lib.m3r_peer_wait(C.c_void_p(flags.data_ptr()), 1 << 2, 5, sp), "peer_wait")
+    torch.cuda.synchronize()
+    assert all(torch.equal(d, src) for d in dsts) and flags.tolist() == [0, 0, 7, 0, 0, 0, 0, 0]
