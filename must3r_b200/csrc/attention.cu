@@ -25,6 +25,9 @@
 // masked key tiles are never loaded.  Small grids (one view per step) split the key range over several CTAs; the
 // last CTA to finish a (batch, head, query tile) merges the partial (O, m, l) in-kernel.
 #include <math.h>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "ptx.cuh"
 #include "m3r_internal.h"
 
@@ -589,10 +592,10 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK0, const CU
   return 0;
 }
 
-// scratch for the split path, grown on demand (stream-ordered); one per device.  Launches that split must stay on one
-// stream per device at a time (the decoder's side streams never run split attention).
+// scratch for the split path, grown on demand (stream-ordered), one per (device, stream)
 struct SplitScratch { float* buf = nullptr; size_t cap = 0; };
-static SplitScratch g_split[64];
+static std::mutex g_split_mu;
+static std::map<std::pair<int, cudaStream_t>, SplitScratch> g_split;      // per (device, stream): see gemm.cu emit_scratch
 
 }  // namespace m3r
 
@@ -682,7 +685,8 @@ extern "C" int m3r_attention(const m3r_attn_args* a, void* stream) {
     const size_t need = CNT + (size_t)splits * n_cnt * AT_BM * (HD + 2);     // partial O + (m, l), padded to whole query tiles
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return set_error("attention: bad current device");
-    SplitScratch& sc = g_split[dev];
+    std::lock_guard<std::mutex> lock(g_split_mu);
+    SplitScratch& sc = g_split[std::make_pair(dev, cs)];
     if (need > sc.cap) {
       if (sc.buf) cudaFreeAsync(sc.buf, cs);
       sc.buf = nullptr; sc.cap = 0;

@@ -6,6 +6,9 @@
 //                 residual / image2-embed row bias, vectorised global stores
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps the MMAs of
 // tile i+1.  Tiles are walked m-fastest so that co-resident CTAs share the weight tile in L2.
+#include <map>
+#include <mutex>
+#include <utility>
 #include "ptx.cuh"
 #include "m3r_internal.h"
 
@@ -514,17 +517,21 @@ static void fill_params(GemmParams& p, const m3r_gemm_args* a) {
   p.ksplit = 1; p.kpart = nullptr; p.kflag = nullptr;
 }
 
-// Scratch of the LayerNorm-emitting epilogue, one per device: partial row statistics + arrival / departure counters.
-// Only kernels of ONE stream at a time may use it (they spin on each other's CTAs): the model code emits on the
+// Scratch of the LayerNorm-emitting epilogue: partial row statistics + arrival / departure counters (+ split-K hand-over).
+// The CTAs of a launch spin on each other, so launches sharing a scratch must be ordered: the model code emits on the
 // caller's stream only, never on its side streams.
 struct EmitScratch { float2* stats = nullptr; unsigned int* sync = nullptr; float4* kpart = nullptr; unsigned int* kflag = nullptr; };
 constexpr int EMIT_MAX_KSPLIT_TILES = 80;
 constexpr int EMIT_MAX_TILES_M = 16, EMIT_MAX_PARTS = 24;
-static EmitScratch* emit_scratch() {
-  static EmitScratch per_dev[64];
+static EmitScratch* emit_scratch(cudaStream_t stream) {
+  // one scratch per (device, stream): LayerNorm-emitting launches of different streams (two host threads driving the model,
+  // as the reference's SLAM worker does, slam.py:533) must not share counters.  Entries live for the process lifetime.
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, EmitScratch> table;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  EmitScratch& e = per_dev[dev];
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  EmitScratch& e = table[std::make_pair(dev, stream)];
   if (!e.stats) {
     void* a = nullptr; void* b = nullptr;
     if (cudaMalloc(&a, sizeof(float2) * EMIT_MAX_TILES_M * EMIT_MAX_PARTS * BM) != cudaSuccess) return nullptr;
@@ -560,7 +567,7 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream, const m3r_ge
     }
   }
   if constexpr (MODE == MODE_EMIT) {
-    EmitScratch* e = emit_scratch();
+    EmitScratch* e = emit_scratch(stream);
     if (!e) return set_error("gemm: LayerNorm-emit scratch allocation failed");
     p.norm_out = a->norm_out; p.ldn = a->ldn; p.norm_eps = a->norm_eps; p.stats = e->stats; p.sync = e->sync;
     static int ks_env = -1;

@@ -184,8 +184,9 @@ _WS = {}
 
 
 def workspace(device: torch.device, nbytes: int, tag: str) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, tag); kernels of one stream are ordered, so reuse is safe."""
-    key = (str(device), tag)
+    """Grow-only scratch buffer per (device, current stream, tag): kernels of one stream are ordered, so reuse is safe;
+    two host threads driving the model on their own streams (the reference's SLAM worker, slam.py:533) get their own."""
+    key = (str(device), int(torch.cuda.current_stream(device).cuda_stream), tag)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)

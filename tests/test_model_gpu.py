@@ -350,3 +350,14 @@ def test_stream_schedule_inplace_memory_equals_copy_path():
         inf._reserve = real
     assert torch.equal(mem_a[1], mem_b[1]) and all(torch.equal(a, b) for a, b in zip(mem_a[0], mem_b[0]))
     assert all(torch.equal(a[k], b[k]) for a, b in zip(out_a, out_b) for k in a)
+
+
+def test_two_host_threads_on_two_streams():
+    """The reference's SLAM drives the model from a worker thread while another thread owns the main stream (slam.py:533): two
+    host threads running decoder chains at the same time on their own CUDA streams (per-stream workspaces, LayerNorm-emit
+    counters and attention split scratch) must reproduce the single-threaded results bit for bit (tools/two_threads.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "two_threads.py")], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "single thread: True" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
