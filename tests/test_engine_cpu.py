@@ -237,3 +237,29 @@ def test_memory_pickle_roundtrip_in_reference_layout(tmp_path):
     m_a, p_a = dec(x[None], pos[None], ts[None, 5:6], tuple(mem))
     m_b, p_b = dec(x[None], pos[None], ts[None, 5:6], tuple(mem5))
     assert torch.equal(p_a, p_b)
+
+
+def test_rigid_registration_horn_equals_weighted_kabsch():
+    """The cuSOLVER-free rotation (Horn's quaternion solution through repeated 4x4 squaring) against weighted Kabsch via SVD:
+    exact poses, noisy ones, a batch, near-planar clouds and a configuration whose unconstrained optimum is a reflection."""
+    from must3r_b200.engine import camera
+    g = torch.Generator().manual_seed(5)
+    for case in range(8):
+        n = 500
+        x = torch.randn(3, n, 3, generator=g) * torch.tensor([1.0, 1.0, 0.02 if case % 3 == 2 else 1.0])
+        A = torch.randn(3, 3, 3, generator=g)
+        Q, _ = torch.linalg.qr(A)
+        Q = Q * torch.sign(torch.linalg.det(Q))[:, None, None]
+        if case == 5:
+            Q[:, :, 2] *= -1                                           # a reflection: the best PROPER rotation is not Q
+        t0 = torch.randn(3, 3, generator=g)
+        y = x @ Q.transpose(-1, -2) + t0[:, None, :] + (0.05 * torch.randn(3, n, 3, generator=g) if case % 2 else 0.0)
+        w = torch.rand(3, n, generator=g) + 0.1
+        Rh, th = camera.rigid_points_registration(x, y, w)
+        Rs, ts_ = camera.rigid_points_registration(x, y, w, method="svd")
+        assert torch.allclose(torch.linalg.det(Rh), torch.ones(3), atol=1e-5)
+        assert torch.allclose(Rh @ Rh.transpose(-1, -2), torch.eye(3).expand(3, 3, 3), atol=1e-5)
+        cost = lambda R, t: (w * (x @ R.transpose(-1, -2) + t[:, None] - y).square().sum(-1)).sum(-1)  # noqa: E731
+        assert torch.all(cost(Rh, th) <= cost(Rs, ts_) * (1 + 1e-4) + 1e-6), case     # the same minimum ...
+        if case != 5 and case % 3 != 2:
+            assert torch.allclose(Rh, Rs, atol=2e-4) and torch.allclose(th, ts_, atol=2e-4), case    # ... and the same minimiser when it is unique

@@ -106,6 +106,22 @@ if "longmem" in which:       # one-view update cross-attention against long memo
         fl = 4.0 * B * H * Nq * Nk * 64
         print(f"longmem 1v x M={M_:3d} default {ms0*1e3:8.1f} us ({fl/ms0/1e9:6.1f} TF/s) | best " + "  ".join(f"qt{q_}s{s_}:{m*1e3:.1f}us({fl/m/1e9:.0f})" for m, q_, s_ in res[:4]), flush=True)
 
+if "bnsweep" in which:       # tile width of the one-wave GEMMs of the one-view / two-view steps (warm L2, like inside a step)
+    import os as _os
+    for name, (M, N, K, act) in {"merged qkv|kv 1v": (768, 3840, 768, "none"), "fc1 1v": (768, 3072, 768, "gelu"), "q 1v": (768, 768, 768, "none"),
+                                 "head 1v": (768, 1792, 768, "none"), "merged 2v": (1536, 3840, 768, "none"), "fc1 2v": (1536, 3072, 768, "gelu"),
+                                 "merged 224 1v": (196, 3840, 768, "none"), "fc1 224 1v": (196, 3072, 768, "gelu")}.items():
+        a = torch.randn(M, K, device="cuda").to(dt); w = (torch.randn(N, K, device="cuda") / 28).to(dt)
+        out = torch.empty(M, N, device="cuda", dtype=torch.float32 if name.startswith("head") else dt)
+        res = []
+        for bn in (32, 64, 128, 160, 192, 256):
+            if N % bn: continue
+            _os.environ["M3R_GEMM_BN"] = str(bn)
+            res.append((timeit(lambda: ops.linear(a, w, None, act=act, out=out, w_static=True), iters=15), bn))
+        _os.environ.pop("M3R_GEMM_BN")
+        ms0 = timeit(lambda: ops.linear(a, w, None, act=act, out=out, w_static=True), iters=15)
+        print(f"bnsweep {name:16s} M={M} N={N} K={K}: default {ms0*1e3:.1f}us | " + "  ".join(f"BN{b}:{m*1e3:.1f}" for m, b in res), flush=True)
+
 if "small" in which:
     import os as _os
     for name, (M, N, K) in {"dec qkv 1v": (768, 2304, 768), "dec proj 1v": (768, 768, 768), "dec kv 1v": (768, 1536, 768),
