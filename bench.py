@@ -244,6 +244,9 @@ def main():
     ap.add_argument("--no-records", action="store_true", help="skip the extra configurations (records)")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--stream-frames", type=int, default=1000)
+    ap.add_argument("--encoder-mode", default="precomputed", choices=["engine", "precomputed"],
+                    help="precomputed (default): engine.encoder_multi_ar over all views first, then the decoder chain; engine: the engine "
+                         "encodes the views itself (encoder_precomputed_features=None) on a side stream next to the chain (look-ahead)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -330,8 +333,8 @@ def main():
         def job(from_host=False, to_host=False, post=pp):
             imgs = state["pinned"].to(dev, non_blocking=True) if from_host else state["dev"]
             views, tss = list(imgs.unbind(0)), list(ts.unbind(0))          # true_shape stays on the host, as an image loader yields it
-            x, pos = engine.encoder_multi_ar(enc, views, ts, device=dev, max_bs=50)
-            _, pm = engine.inference_multi_ar(enc, dec, views, ids, tss, [2] + [1] * (V - 2), encoder_precomputed_features=(x, pos),
+            feats = engine.encoder_multi_ar(enc, views, ts, device=dev, max_bs=50) if args.encoder_mode == "precomputed" else None
+            _, pm = engine.inference_multi_ar(enc, dec, views, ids, tss, [2] + [1] * (V - 2), encoder_precomputed_features=feats,
                                               post_process_function=post, device=dev, preserve_gpu_mem=to_host)
             return pm
         upd, ren = chain_schedule(V)
@@ -373,8 +376,8 @@ def main():
 
         def job(from_host=False, to_host=False, post=pp):
             views, tss = list(state["dev"].unbind(0)), list(ts.unbind(0))
-            x, pos = engine.encoder_multi_ar(enc, views, ts, device=dev, max_bs=50)
-            return engine.inference_video_multi_ar(enc, dec, views, tss, [2] + [1] * (frames - 2), encoder_precomputed_features=(x, pos),
+            feats = engine.encoder_multi_ar(enc, views, ts, device=dev, max_bs=50) if args.encoder_mode == "precomputed" else None
+            return engine.inference_video_multi_ar(enc, dec, views, tss, [2] + [1] * (frames - 2), encoder_precomputed_features=feats,
                                                    post_process_function=post, device=dev, local_context_size=25,
                                                    preserve_gpu_mem=to_host)
         # keyframes (every 3rd) stay, plus the <= 25 most recent frames: frame t attends ~ t/3 + min(t, 25)*2/3 views
@@ -633,7 +636,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "strong" if args.config == "c4" else "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": cfg["label"] + (", random-init ViT-L enc / ViT-B dec" if True else ""), "config_id": args.config,
-                       "global_views": meta["views"], "parallelism": par,
+                       "global_views": meta["views"], "parallelism": par, "encoder_mode": args.encoder_mode,
                        "l2": "working set (1.7 GB of 16-bit weights + activations + memory tokens) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": meta["views"] / (ms_e2e / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e},
