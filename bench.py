@@ -245,8 +245,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--stream-frames", type=int, default=1000)
     ap.add_argument("--encoder-mode", default="precomputed", choices=["engine", "precomputed"],
-                    help="precomputed (default): engine.encoder_multi_ar over all views first, then the decoder chain; engine: the engine "
-                         "encodes the views itself (encoder_precomputed_features=None) on a side stream next to the chain (look-ahead)")
+                    help="precomputed (default): engine.encoder_multi_ar over all views first, then the decoder chain (features handed to "
+                         "the engine); engine: encoder_precomputed_features=None, the engine encodes the missing views itself (up front, batched)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

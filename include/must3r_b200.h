@@ -36,10 +36,6 @@ extern "C" {
 
 const char* m3r_last_error(void);
 int m3r_abi_version(void);
-/* CTA cap (0 = none) for the persistent GEMM kernels launched by the CALLING THREAD from now on: lets a throughput-bound call
- * (the encoder of upcoming views, on a side stream) share the device with the latency-bound decoder chain instead of holding
- * every SM.  The LayerNorm-emitting GEMMs ignore it (they need all their tiles co-resident). */
-void m3r_set_sm_budget(int32_t n_ctas);
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long long m3r_launch_count(void);
 /* Optional per-kernel device timing for bench.py: CUDA events are recorded on the launch stream around every

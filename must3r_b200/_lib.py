@@ -60,7 +60,6 @@ SIGNATURES = {
     "m3r_abi_version": (C.c_int, []),
     "m3r_debug_trace": (C.c_int, [C.c_void_p]),
     "m3r_launch_count": (C.c_longlong, []),
-    "m3r_set_sm_budget": (None, [C.c_int32]),
     "m3r_prof_enable": (None, [C.c_int]),
     "m3r_prof_read": (C.c_int, [C.POINTER(C.c_double)]),
     "m3r_gemm": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),

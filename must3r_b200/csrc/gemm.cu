@@ -586,7 +586,6 @@ static int launch_gemm(const m3r_gemm_args* a, cudaStream_t stream, const m3r_ge
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (MODE == MODE_EMIT) grid = tiles * p.ksplit;
   if (MODE == MODE_GROUPED && grp->max_ctas > 0 && grid > grp->max_ctas) grid = grp->max_ctas;
-  if (MODE != MODE_EMIT && sm_budget() > 0 && grid > sm_budget()) grid = sm_budget();      // persistent tile loop: any grid size works
   if (MODE == MODE_EMIT && grid > num_sms()) return set_error("gemm: LayerNorm-emitting epilogue needs one tile per CTA (%d tiles, %d SMs)", tiles, grid);
   {
     const int cat = BN >= 256 ? PROF_GEMM256 : (BN >= 128 ? PROF_GEMM128 : PROF_GEMM64);
@@ -753,7 +752,6 @@ static int launch_gemm_pair(const m3r_gemm_args* a, cudaStream_t stream) {
   }
   const int tiles = ((a->M + 255) / 256) * (a->N / 256);
   int pairs = num_sms() / 2;
-  if (sm_budget() > 0 && pairs > sm_budget() / 2) pairs = sm_budget() / 2 > 0 ? sm_budget() / 2 : 1;
   if (tiles < pairs) pairs = tiles;
   {
     ProfScope prof(PROF_GEMM256, 2.0 * a->M * (double)a->N * a->K, 2.0 * ((double)a->M * a->K + (double)a->N * a->K) + (double)a->M * a->N * (a->out_dtype ? 2 : 4), stream);

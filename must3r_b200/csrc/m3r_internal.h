@@ -10,7 +10,6 @@ namespace m3r {
 
 int set_error(const char* fmt, ...);           // records the message, returns 1
 int num_sms();                                  // SM count of the current device (cached)
-int sm_budget();                                // > 0: CTA cap for this thread's persistent GEMM launches (m3r_set_sm_budget)
 void count_launch();                            // bumps the kernel-launch counter (m3r_launch_count)
 
 // Optional per-category device timing (m3r_prof_*): CUDA events recorded on the launch stream around each kernel.

@@ -59,12 +59,6 @@ int num_sms() {
   return sms[dev];
 }
 
-// SM budget of the calling thread's persistent GEMM launches (0 = whole device): the engine runs the encoder of upcoming views
-// on a low-priority side stream NEXT to the latency-bound decoder chain; its persistent GEMM CTAs would otherwise hold every
-// SM for ~100 us at a time and starve the chain's one-wave kernels.
-static thread_local int g_sm_budget = 0;
-int sm_budget() { return g_sm_budget; }
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -122,7 +116,6 @@ int make_tmap_3d(CUtensorMap* out, const void* base, int is_bf16, uint64_t cols,
 }  // namespace m3r
 
 extern "C" const char* m3r_last_error(void) { return m3r::g_err; }
-extern "C" void m3r_set_sm_budget(int32_t n) { m3r::g_sm_budget = n > 0 ? n : 0; }
 extern "C" int m3r_abi_version(void) { return M3R_ABI_VERSION; }
 extern "C" long long m3r_launch_count(void) { return m3r::g_launches.load(); }
 

@@ -431,108 +431,35 @@ def _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device):
     return xi, pi
 
 
-# --------------------------------------------------------------------------------------------- encoder look-ahead
+# --------------------------------------------------------------------------------------------- missing encoder features
 # When the caller leaves the encoding to the engine (encoder_precomputed_features=None: what the reference's demo does,
 # must3r/demo/inference.py:198), the reference encodes each step's views right before the decoder call
-# (engine/inference.py:270-276,400-406).  The decoder chain of one-view updates is latency-bound and leaves most SMs idle,
-# the encoder is throughput-bound: here the features of ALL upcoming views are produced on a side stream, in schedule order
-# and in batches, with the encoder's persistent GEMMs capped to a share of the SMs (Dust3rEncoder.sm_budget), while the
-# chain runs on the caller's stream; each step only waits for the event of its own views' batch.  Same kernels, same
-# per-view results (rows are independent), different overlap.
-_LOOKAHEAD_STREAMS = {}
-_CHAIN_STREAMS = {}
-LOOKAHEAD_BATCH = int(__import__("os").environ.get("M3R_LOOKAHEAD_BATCH", "4"))      # views per look-ahead encoder call
-LOOKAHEAD_SM_BUDGET = int(__import__("os").environ.get("M3R_LOOKAHEAD_SMS", "64"))   # SMs its GEMMs may hold next to the chain (of 148)
+# (engine/inference.py:270-276,400-406): one ViT-L pass per view, M = 768 rows, far below the GEMMs' efficient size.  With the
+# CUDA encoder the missing views are encoded UP FRONT, in large same-shape batches, then the decoder chain runs: measured on
+# C3 63.3 ms vs 88.7 ms for per-step encoding.  (Encoding on a side stream NEXT to the latency-bound chain - SM-capped
+# persistent GEMMs, chain on a high-priority stream - was measured too and lost: 70.5 .. 93.9 ms, the chain's one-wave kernels
+# wait for SMs; profiles/r02_run17_*, r02_run18_*.)  Same kernels, same per-view features (rows are independent).
+ENCODE_AHEAD_BATCH = 50
 
 
-def _lookahead_wanted(encoder, encoder_precomputed_features, device):
+def _encode_missing_upfront(encoder, imgs, true_shape, x, pos, device, max_bs=None):
+    """Fill x / pos for every view whose features are missing, in batches of views with one true_shape (CUDA encoder only)."""
     import os
-    return (encoder_precomputed_features is None and str(device).startswith("cuda") and hasattr(encoder, "sm_budget")
-            and os.environ.get("M3R_LOOKAHEAD", "1") != "0")
-
-
-class _ChainPriority:
-    """While the encoder look-ahead shares the device, the latency-bound decoder chain runs on a HIGH-priority stream (its CTAs
-    are dispatched before the encoder's whenever an SM frees up); the caller's stream waits for it at the end."""
-
-    def __init__(self, device, active):
-        self.dev, self.active = torch.device(device) if active else None, active
-
-    def __enter__(self):
-        if not self.active or __import__("os").environ.get("M3R_LOOKAHEAD_PRIO", "1") == "0":
-            self.active = False
-            return self
-        self.prev = torch.cuda.current_stream(self.dev)
-        hp = _CHAIN_STREAMS.get(self.dev.index)
-        if hp is None:
-            hp = _CHAIN_STREAMS[self.dev.index] = torch.cuda.Stream(device=self.dev, priority=-1)
-        self.hp = hp
-        hp.wait_stream(self.prev)
-        torch.cuda.set_stream(hp)
-        return self
-
-    def __exit__(self, *a):
-        if self.active:
-            torch.cuda.set_stream(self.prev)
-            self.prev.wait_stream(self.hp)
-        return False
-
-
-def _encoder_lookahead(encoder, imgs, true_shape, x, pos, n_first, device, max_bs=None):
-    """Enqueue the encoder for every view whose features are missing; -> {view index: event to wait for} (or None)."""
-    if not _lookahead_wanted(encoder, None, device):
-        return None
+    if not str(device).startswith("cuda") or not getattr(encoder, "batches_well", False) or os.environ.get("M3R_ENCODE_AHEAD", "1") == "0":
+        return
     missing = [i for i in range(len(x)) if x[i] is None or pos[i] is None]
-    if len(missing) <= n_first:
-        return None
-    dev = torch.device(device)
-    st = _LOOKAHEAD_STREAMS.get(dev.index)
-    if st is None:
-        st = _LOOKAHEAD_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
-    main = torch.cuda.current_stream(dev)
-    st.wait_stream(main)                                   # the images are ready
-    bs = min(LOOKAHEAD_BATCH, max_bs) if max_bs else LOOKAHEAD_BATCH
-    head = [i for i in missing if i < n_first]             # the first decoder call's views: one batch, encoded at full speed
-    batches = [head] if head else []
-    cur = []
+    if len(missing) < 2:
+        return
+    bs = min(ENCODE_AHEAD_BATCH, max_bs) if max_bs else ENCODE_AHEAD_BATCH
+    groups = {}
     for i in missing:
-        if i < n_first:
-            continue
-        if cur and (len(cur) >= bs or not torch.equal(true_shape[i], true_shape[cur[0]])):
-            batches.append(cur)
-            cur = []
-        cur.append(i)
-    if cur:
-        batches.append(cur)
-    if head and any(not torch.equal(true_shape[i], true_shape[head[0]]) for i in head):
-        return None                                        # mixed aspect ratios in the first call: leave it to the per-step path
-    events = {}
-    for k, b in enumerate(batches):
-        with torch.cuda.stream(st):
-            # the first block (the views of the first decoder call) has the device to itself; later ones share it with the chain
-            encoder.sm_budget = 0 if (k == 0 and head) else LOOKAHEAD_SM_BUDGET
-            try:
-                xs, ps = encoder(torch.stack([imgs[i] for i in b]).to(dev, non_blocking=True), torch.stack([true_shape[i] for i in b]).to(dev))
-            finally:
-                encoder.sm_budget = 0
-            ev = torch.cuda.Event()
-            ev.record(st)
-        xs.record_stream(main)
-        ps.record_stream(main)
-        for j, v in enumerate(b):
-            x[v], pos[v], events[v] = xs[j], ps[j], ev
-    return events
-
-
-def _wait_features(events, views):
-    """Make the current stream wait for the look-ahead batches holding these views' features."""
-    if events:
-        seen = set()
-        for v in views:
-            ev = events.get(int(v))
-            if ev is not None and id(ev) not in seen:
-                torch.cuda.current_stream().wait_event(ev)
-                seen.add(id(ev))
+        groups.setdefault(tuple(int(v) for v in true_shape[i].tolist()), []).append(i)
+    for ids in groups.values():
+        for lo in range(0, len(ids), bs):
+            b = ids[lo:lo + bs]
+            xs, ps = encoder(torch.stack([imgs[i] for i in b]).to(device), torch.stack([true_shape[i] for i in b]).to(device))
+            for j, v in enumerate(b):
+                x[v], pos[v] = xs[j], ps[j]
 
 
 def _default_is_keyframe(id, res, scene_state):
@@ -566,14 +493,13 @@ def inference_video_multi_ar(encoder, decoder, imgs, true_shape, mem_batches, ve
                         or scene_state_update_function is not _default_scene_state_update)
     window = deque()
     _reserve(decoder, 0, 1.5)                  # CUDA decoder: memory buffers grow geometrically, updates append in place
-    feat_events = _encoder_lookahead(encoder, imgs, true_shape, x, pos, int(bounds[1]), device, max_bs)
+    _encode_missing_upfront(encoder, imgs, true_shape, x, pos, device, max_bs)
     for _ in range(num_refinements_iterations + 1):
         window = deque()
         for step in range(len(bounds) - 1):
             lo, hi = bounds[step], bounds[step + 1]
             ts_i, imgs_i, ids_i = true_shape[lo:hi], imgs[lo:hi], list(range(lo, hi))
             x_i, pos_i = _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device)
-            _wait_features(feat_events, range(lo, hi))
             ts_st, idx_st, x_st, pos_st, img_st = stack_views(ts_i, [x_i, pos_i, imgs_i], max_bs=max_bs)
             n_before = get_Nmem(mem)
             mem_prev = mem
@@ -640,16 +566,6 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
                        num_refinements_iterations=0):
     """Build the memory from the first sum(mem_batches) views, optionally refine it, then render
     (engine/inference.py:369-527)."""
-    dev = device or true_shape[0].device
-    with _ChainPriority(dev, precomputed_mem is None and _lookahead_wanted(encoder, encoder_precomputed_features, dev)):
-        return _inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches, verbose, max_bs, to_render,
-                                   encoder_precomputed_features, precomputed_mem, preserve_gpu_mem, post_process_function, device,
-                                   return_mem, viser_server, num_refinements_iterations)
-
-
-def _inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches, verbose, max_bs, to_render,
-                        encoder_precomputed_features, precomputed_mem, preserve_gpu_mem, post_process_function, device,
-                        return_mem, viser_server, num_refinements_iterations):
     true_shape = torch.stack(true_shape, dim=0)
     n = true_shape.shape[0]
     device = device or true_shape.device
@@ -661,7 +577,7 @@ def _inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches
         label_of = {}
         # CUDA decoder: size the memory buffers once for the whole schedule, every update then appends in place
         known = [v for v in x[:bounds[-1]] if v is not None]
-        feat_events = _encoder_lookahead(encoder, imgs, true_shape, x, pos, int(bounds[1]), device, max_bs)
+        _encode_missing_upfront(encoder, imgs, true_shape, x, pos, device, max_bs)
         known = [v for v in x[:bounds[-1]] if v is not None]
         if len(known) == bounds[-1]:
             _reserve(decoder, sum(int(v.shape[-2]) for v in known), 0.0)
@@ -672,7 +588,6 @@ def _inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches
                 lo, hi = bounds[step], bounds[step + 1]
                 ts_i, imgs_i, ids_i = true_shape[lo:hi], imgs[lo:hi], img_ids[lo:hi]
                 x_i, pos_i = _ensure_features(encoder, x, pos, imgs, true_shape, lo, hi, max_bs, device)
-                _wait_features(feat_events, range(lo, hi))
                 ts_st, idx_st, x_st, pos_st, img_st = stack_views(ts_i, [x_i, pos_i, imgs_i], max_bs=max_bs)
                 refresh = all(int(v) in label_of for v in ids_i)     # all views already stored: refinement step
                 new_mem, res = _multi_ar_batch(encoder, decoder, img_st, ts_st, mem, verbose=verbose,
@@ -702,8 +617,8 @@ def _inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches
                     viser_server.set_views(ids_i, imgs_i, res, [True] * len(imgs_i))
         _reserve(decoder)
     else:
-        first_pass, mem, feat_events = None, precomputed_mem, None
-    _wait_features(feat_events, range(n))              # the render pass needs every view's features
+        first_pass, mem = None, precomputed_mem
+        _encode_missing_upfront(encoder, imgs, true_shape, x, pos, device, max_bs)
 
     if to_render is not None:
         x, pos = [x[v] for v in to_render], [pos[v] for v in to_render]

@@ -110,7 +110,7 @@ class Dust3rEncoder(nn.Module):
             self._pos_cache[key] = torch.cartesian_prod(torch.arange(h, device=device), torch.arange(w, device=device))
         return self._pos_cache[key]
 
-    sm_budget = 0      # > 0: this encoder's persistent GEMMs use at most that many SMs (engine look-ahead next to the decoder chain)
+    batches_well = True     # one call over many views is far more efficient than one call per view (engine: encode missing views up front)
 
     # ---- forward -------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -156,16 +156,9 @@ class Dust3rEncoder(nn.Module):
         out = torch.empty((V, N, self.embed_dim), dtype=torch.float32, device=img.device)
         nbytes = lib.m3r_encoder_workspace_bytes(C.byref(w), V, H, W)
         with torch.cuda.device(img.device):
-            budget = int(getattr(self, "sm_budget", 0) or 0)
-            if budget:
-                lib.m3r_set_sm_budget(budget)            # thread-local: this call's persistent GEMMs use at most `budget` SMs
-            try:
-                ws = cm.workspace(img.device, nbytes, "enc")
-                _lib.check(lib.m3r_encoder_forward(C.byref(w), C.c_void_p(img.data_ptr()), V, H, W, C.c_void_p(pos1.data_ptr()),
-                                                   C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
-                                                   cm.stream_ptr(img.device)), "encoder_forward")
-            finally:
-                if budget:
-                    lib.m3r_set_sm_budget(0)
+            ws = cm.workspace(img.device, nbytes, "enc")
+            _lib.check(lib.m3r_encoder_forward(C.byref(w), C.c_void_p(img.data_ptr()), V, H, W, C.c_void_p(pos1.data_ptr()),
+                                               C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                               cm.stream_ptr(img.device)), "encoder_forward")
         return out, pos1.view(1, N, 2).expand(V, -1, -1).clone()
 
