@@ -9,7 +9,7 @@ dust3r/dust3r/utils/path_to_croco.py:36-42).  Install it with::
     sys.modules["curope"] = shim          # before the first `import must3r` / `import dust3r`
 
 or copy this file next to the checkout as ``curope.py``.  Same operator contract as curope.cpp:49-69: float base and
-fwd (F0, negative for the backward rotation), RuntimeError for bad shapes, fp32 / fp16 / bf16 tokens; unlike the
+fwd (F0; a negative value rotates backwards), RuntimeError for bad shapes, fp32 / fp16 / bf16 tokens; unlike the
 reference launcher (kernels.cu:102) the kernel runs on the caller's current CUDA stream.  CUDA tensors only - there is
 no CPU path here (the reference's curope.cpp:17-47 CPU loop has no counterpart; use the PyTorch fallback on CPU).
 """
@@ -22,32 +22,18 @@ def rope_2d(tokens, positions, base, fwd):
     ops.rope_2d(tokens, positions, float(base), float(fwd))
 
 
-class cuRoPE2D_func(torch.autograd.Function):
-    """dust3r/croco/models/curope/curope2d.py:12-29 (forward rotates by +F0 in place, backward by -F0)."""
-
-    @staticmethod
-    def forward(ctx, tokens, positions, base, F0=1):
-        ctx.save_for_backward(positions)
-        ctx.saved_base, ctx.saved_F0 = base, F0
-        rope_2d(tokens, positions, base, F0)
-        ctx.mark_dirty(tokens)
-        return tokens
-
-    @staticmethod
-    def backward(ctx, grad_res):
-        positions, base, F0 = ctx.saved_tensors[0], ctx.saved_base, ctx.saved_F0
-        rope_2d(grad_res, positions, base, -F0)
-        ctx.mark_dirty(grad_res)
-        return grad_res, None, None, None
-
-
 class cuRoPE2D(torch.nn.Module):
-    """dust3r/croco/models/curope/curope2d.py:32-39: tokens [B,H,N,D] rotated in place through a [B,N,H,D] view."""
+    """Drop-in for the module the reference builds through `get_pos_embed` (must3r/model/blocks/pos_embed.py:7-22): rotates
+    q / k of shape [B, heads, N, D] IN PLACE through a [B, N, heads, D] view and hands the same tensor back
+    (dust3r/croco/models/curope/curope2d.py:32-39).  Inference only: the reference wraps the call in an autograd Function whose
+    backward is the rotation by -F0; this path has no training loop, so gradients are refused loudly instead of being wrong."""
 
     def __init__(self, freq=100.0, F0=1.0):
         super().__init__()
         self.base, self.F0 = freq, F0
 
     def forward(self, tokens, positions):
-        cuRoPE2D_func.apply(tokens.transpose(1, 2), positions, self.base, self.F0)
+        if tokens.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("must3r_b200.compat.curope is inference-only (run under torch.no_grad())")
+        rope_2d(tokens.transpose(1, 2), positions, self.base, self.F0)
         return tokens

@@ -580,7 +580,10 @@ def inference_multi_ar(encoder, decoder, imgs, img_ids, true_shape, mem_batches,
         _encode_missing_upfront(encoder, imgs, true_shape, x, pos, device, max_bs)
         known = [v for v in x[:bounds[-1]] if v is not None]
         if len(known) == bounds[-1]:
-            _reserve(decoder, sum(int(v.shape[-2]) for v in known), 0.0)
+            # (a refinement pass re-runs every step against the full memory: keep room for the largest step's rows, which
+            # the engine hands back after copying the refreshed ones - _release_tail)
+            steps = [sum(int(v.shape[-2]) for v in known[bounds[k]:bounds[k + 1]]) for k in range(len(bounds) - 1)]
+            _reserve(decoder, sum(steps) + (max(steps) if num_refinements_iterations > 0 else 0), 0.0)
         else:
             _reserve(decoder, 0, 1.5)
         for _ in range(num_refinements_iterations + 1):

@@ -263,3 +263,67 @@ def test_rigid_registration_horn_equals_weighted_kabsch():
         assert torch.all(cost(Rh, th) <= cost(Rs, ts_) * (1 + 1e-4) + 1e-6), case     # the same minimum ...
         if case != 5 and case % 3 != 2:
             assert torch.allclose(Rh, Rs, atol=2e-4) and torch.allclose(th, ts_, atol=2e-4), case    # ... and the same minimiser when it is unique
+
+
+class _ArenaOracleDecoder:
+    """The oracle decoder behind the growable-memory contract of the CUDA decoder (model/decoder.py MemArena, reserve_memory):
+    update calls whose input is the latest version of an arena with room left append their rows in place, everything else
+    gets a fresh arena and a copy.  Lets the CPU suite drive the engine's arena-aware memory edits (tail drops, in-place
+    compaction, keyframe refresh, released tails) that otherwise only run on the GPU."""
+
+    def __init__(self, dec):
+        self.dec, self._reserve_tokens, self._growth = dec, 0, 0.0
+        self.inplace_appends = self.fresh_arenas = 0
+
+    def reserve_memory(self, n_tokens=0, growth=0.0):
+        self._reserve_tokens, self._growth = int(n_tokens), float(growth)
+
+    def __call__(self, x, pos, true_shape, current_mem=None, render=False):
+        from must3r_b200.model.decoder import MemArena
+        new_mem, pms = self.dec(x, pos, true_shape, current_mem, render=render)
+        if render:
+            return current_mem, pms
+        Nm = 0 if current_mem is None else current_mem[0][0].shape[1]
+        rows = new_mem[0][0].shape[1]
+        arena = MemArena.of(current_mem[0]) if Nm > 0 else None
+        if arena is None or arena.tail != Nm or rows > arena.cap:
+            cap = max(rows, self._reserve_tokens, int(rows * self._growth))
+            arena = MemArena([torch.full((v.shape[0], cap, v.shape[2]), float("nan")) for v in new_mem[0]], cap)
+            for buf, v in zip(arena.bufs, new_mem[0]):
+                buf[:, :Nm] = v[:, :Nm]
+            self.fresh_arenas += 1
+        else:
+            self.inplace_appends += 1
+        for buf, v in zip(arena.bufs, new_mem[0]):
+            buf[:, Nm:rows] = v[:, Nm:]
+        arena.tail = rows
+        return (arena.views(rows), new_mem[1]) + tuple(new_mem[2:]), pms
+
+
+@pytest.mark.parametrize("schedule", ["video", "offline"])
+def test_engine_memory_edits_on_growable_buffers(schedule):
+    """Streaming schedule (window eviction from the middle of the memory, non-keyframe tail drops, a refinement pass with
+    keyframe refresh) and offline schedule (refinement: discarded appended tails) on in-place growing memory buffers: results
+    and final memory equal the plain per-call concatenation, and the appends really happen in place."""
+    enc, dec = tiny_oracle(7)
+    F = 12
+    imgs, ts = syn.synthetic_views(F, 32, 48, seed=61)
+    views, tss = list(imgs.unbind(0)), list(ts.unbind(0))
+    raw = lambda p: {"raw": p}  # noqa: E731
+    arena_dec = _ArenaOracleDecoder(dec)
+    if schedule == "video":
+        kw = dict(post_process_function=raw, device="cpu", return_mem=True, local_context_size=3, num_refinements_iterations=1)
+        mem_a, out_a = engine.inference_video_multi_ar(enc, arena_dec, views, tss, [2] + [1] * (F - 2), **kw)
+        mem_b, out_b = engine.inference_video_multi_ar(enc, dec, views, tss, [2] + [1] * (F - 2), **kw)
+    else:
+        ids = [torch.tensor(i) for i in range(F)]
+        kw = dict(post_process_function=raw, device="cpu", return_mem=True, num_refinements_iterations=1)
+        mem_a, _, out_a = engine.inference_multi_ar(enc, arena_dec, views, ids, tss, [2, 1, 1, 2, 1], **kw)
+        mem_b, _, out_b = engine.inference_multi_ar(enc, dec, views, ids, tss, [2, 1, 1, 2, 1], **kw)
+    assert torch.equal(mem_a[1], mem_b[1]) and [int(v) for v in mem_a[2:]] == [int(v) for v in mem_b[2:]]
+    for a, b in zip(mem_a[0], mem_b[0]):
+        assert torch.equal(a, b)
+    for a, b in zip(out_a, out_b):
+        assert torch.equal(a["raw"], b["raw"])
+    # (on CPU the features are encoded step by step, so the engine cannot size the buffers up front: geometric growth 1.5x)
+    assert arena_dec.inplace_appends >= 2 * arena_dec.fresh_arenas, (arena_dec.inplace_appends, arena_dec.fresh_arenas)
