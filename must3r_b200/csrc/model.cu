@@ -136,6 +136,19 @@ struct SideStream {
     return r == cudaSuccess ? 0 : set_error("decoder_forward: stream fork/join failed: %s", cudaGetErrorString(r));
   }
 };
+// Joins whatever was forked onto the side / copy streams when the enclosing call returns early (an M3R_TRY error path):
+// the caller's stream must never be left without a dependency on work that touches its buffers.
+struct SideJoin {
+  SideStream* sd = nullptr;
+  cudaStream_t cs = nullptr;
+  bool forked = false, copying = false, done = false;
+  ~SideJoin() {
+    if (done || !sd) return;
+    if (forked) sd->link(sd->s, cs);
+    if (copying) sd->link(sd->copy, cs);
+  }
+};
+
 static SideStream* side_streams() {
   static SideStream per_dev[64];
   int dev = 0;
@@ -254,6 +267,8 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
   SideStream* sd = store_new ? side_streams() : nullptr;
   if (sd) sd->init();
   const bool side = sd && sd->ok;
+  SideJoin join_guard;
+  if (side) { join_guard.sd = sd; join_guard.cs = cs; }
   if (store_new && Nm > 0 && !c->new_only) {
     // old memory rows -> output memory tensors (the reference's torch.cat, decoder.py:330) unless the caller appends in
     // place (mem_out[l] == mem[l]); independent of the whole step: copy stream, joined at the end
@@ -262,7 +277,7 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     for (int l = 0; l < depth; ++l) {
       if (!c->mem_out[l]) return set_error("decoder_forward: mem_out[%d] is null", l);
       if (c->mem[l] == c->mem_out[l]) continue;
-      if (side && !linked) { M3R_TRY(sd->link(cs, cps)); linked = true; }
+      if (side && !linked) { M3R_TRY(sd->link(cs, cps)); linked = true; join_guard.copying = true; }
       cudaError_t e = cudaSuccess;
       if (c->mem_bstride_rows == 0 && B > 1) {            // stride-0 (expanded) memory: one source block for every scene
         for (int bb = 0; bb < B && e == cudaSuccess; ++bb)
@@ -397,6 +412,7 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
     appended = true;
     if (!side) return 0;                                  // without a side stream the append runs after the head
     M3R_TRY(sd->link(cs, sd->s));
+    join_guard.forked = true;
     return append_memory(sd->s);
   };
   M3R_TRY(maybe_append(0));
@@ -516,5 +532,6 @@ extern "C" int m3r_decoder_forward(const m3r_decoder_weights* w, const m3r_decod
       if (Nm > 0 && !c->new_only) M3R_TRY(sd->link(sd->copy, cs));  // and the old-memory copies
     }
   }
+  join_guard.done = true;
   return 0;
 }
